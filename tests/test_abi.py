@@ -1,0 +1,83 @@
+"""CPU: the C-ABI library loads, exports every symbol include/tfa_b200.h declares, and rejects bad
+arguments with the documented codes before touching any device (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "tfa_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tfa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    names = declared_functions()
+    for n in ("tfa_fwd", "tfa_fwd_ex", "tfa_fwd_host", "tfa_error_string", "tfa_abi_version",
+              "tfa_launch_count", "tfa_debug_record", "tfa_selftest_tma", "tfa_selftest_umma"):
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol(built):
+    import tfa_ctypes
+    L = ctypes.CDLL(tfa_ctypes.LIB_PATH)
+    for n in declared_functions():
+        assert hasattr(L, n), f"{n} declared in include/tfa_b200.h but not exported"
+
+
+def test_abi_version_and_error_strings(built):
+    import tfa_ctypes
+    L = tfa_ctypes.lib()
+    assert L.tfa_abi_version() == 1
+    assert L.tfa_error_string(0) == b"success"
+    for code in range(-8, 0):
+        assert L.tfa_error_string(code).startswith(b"tfa:")
+
+
+def test_argument_validation_without_device(built):
+    import tfa_ctypes
+    L = tfa_ctypes.lib()
+    buf = ctypes.create_string_buffer(4096 + 16)
+    base = (ctypes.addressof(buf) + 15) & ~15
+    ok = ctypes.c_void_p(base)
+    bad_align = ctypes.c_void_p(base + 2)
+    f = lambda **kw: L.tfa_fwd(kw.get("q", ok), ok, ok, ok, None, kw.get("B", 1), kw.get("H", 1), kw.get("S", 128),
+                               kw.get("D", 64), kw.get("dtype", 0), 0, 1.0, None)
+    assert f(q=None) == -1            # TFA_EINVAL_PTR
+    assert f(q=bad_align) == -1
+    assert f(D=96) == -2              # TFA_EINVAL_DIM
+    assert f(D=256) == -2
+    assert f(B=0) == -3               # TFA_EINVAL_SHAPE
+    assert f(S=0) == -3
+    assert f(dtype=2) == -4           # TFA_EINVAL_DTYPE
+    # host path validates the same way
+    assert L.tfa_fwd_host(None, ok, ok, ok, None, 1, 1, 128, 64, 0, 0, 1.0, 1) == -1
+    assert L.tfa_fwd_host(ok, ok, ok, ok, None, 1, 1, 128, 80, 0, 0, 1.0, 1) == -2
+    assert L.tfa_fwd_ex(None) == -1
+
+
+def test_no_fallback_on_cpu_only_box(built):
+    """Without a CUDA device a well-formed call must FAIL (arch/driver error), never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import tfa_ctypes
+    L = tfa_ctypes.lib()
+    buf = ctypes.create_string_buffer(1 << 16)
+    base = ctypes.c_void_p((ctypes.addressof(buf) + 15) & ~15)
+    rc = L.tfa_fwd(base, base, base, base, None, 1, 1, 128, 64, 0, 0, 1.0, None)
+    assert rc != 0
+
+
+def test_product_path_never_imports_oracle():
+    """The shipped package must not reference oracle/ in any way."""
+    pkg = os.path.join(ROOT, "tiny-flash-attention_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "attn_oracle" not in txt, fn

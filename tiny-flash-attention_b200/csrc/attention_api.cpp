@@ -1,0 +1,133 @@
+// attention_api.cpp -- the PyTorch-extension face of the library: Python module `attention_cutlass`.
+//
+// Mirrors the reference's operator surface so its own driver runs unchanged:
+//   /root/reference/flash_attention_cutlass/csrc/attention_api.cpp:6-10   (PYBIND11_MODULE, one m.def)
+//   /root/reference/flash_attention_cutlass/include/attention_api.h:10-11 (signature)
+//   /root/reference/flash_attention_cutlass/csrc/flash_attention.cu:741-772 (host function)
+//   /root/reference/flash_attention_cutlass/test.py:68,80                   (the only caller)
+// i.e.  flash_attention_v2_cutlass(q, k, v, is_causal, softmax_scale) -> [out, softmax_lse]
+// with q,k,v (B,H,S,D) contiguous CUDA fp16/bf16, out like q, softmax_lse (B,H,S) fp32.
+//
+// This file is host glue only: it validates, allocates the outputs with torch, and calls the
+// C ABI (include/tfa_b200.h).  Deliberate differences from the reference:
+//   - launches on the CURRENT stream of q's device, under a device guard (ref: stream 0, no guard);
+//   - no cudaDeviceSynchronize() (ref: flash_attention.cu:768);
+//   - errors raise (TORCH_CHECK) instead of printf + exit(1) (ref: include/attention_api.cuh:20-29);
+//   - dtype other than fp16/bf16 is rejected (ref silently treats everything non-bf16 as fp16, :351);
+//   - bf16 is computed correctly (ref packs P to fp16 bits even in its bf16 branch, :206-215,:601).
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <vector>
+
+#include "../../include/tfa_b200.h"
+
+namespace {
+
+// same wording as the reference's CHECK_INPUT (include/attention_api.cuh:12-18)
+#define TFA_CHECK_CUDA(x) TORCH_CHECK((x).device().is_cuda(), #x " must be a CUDA tensor")
+#define TFA_CHECK_CONTIGUOUS(x) TORCH_CHECK((x).is_contiguous(), #x " must be contiguous")
+#define TFA_CHECK_INPUT(x) \
+  TFA_CHECK_CUDA(x);       \
+  TFA_CHECK_CONTIGUOUS(x)
+
+void check_common(const torch::Tensor& q, const torch::Tensor& k, const torch::Tensor& v) {
+  TORCH_CHECK(q.dim() == 4, "q must have 4 dimensions, got ", q.dim());
+  TORCH_CHECK(q.scalar_type() == at::kHalf || q.scalar_type() == at::kBFloat16,
+              "q must be float16 or bfloat16, got ", q.scalar_type());
+  TORCH_CHECK(k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type(),
+              "q, k, v must have the same dtype");
+  TORCH_CHECK(k.sizes() == q.sizes() && v.sizes() == q.sizes(),
+              "q, k, v must have identical shapes (self-attention, Sq == Sk)");
+  TORCH_CHECK(k.device() == q.device() && v.device() == q.device(), "q, k, v must be on the same device");
+}
+
+void raise_on_error(int rc) {
+  if (rc == 0) return;
+  if (rc == TFA_EDEVICE_FAULT) {
+    unsigned int rec[8];
+    tfa_debug_record(rec);
+    TORCH_CHECK(false, tfa_error_string(rc), " [block ", rec[1], " thread ", rec[2], " site ", rec[3], " iter ", rec[4],
+                " parity ", rec[5], "]");
+  }
+  TORCH_CHECK(false, "attention_cutlass: ", tfa_error_string(rc), " (code ", rc, ")");
+}
+
+std::vector<torch::Tensor> fwd_generic(const torch::Tensor& q, const torch::Tensor& k, const torch::Tensor& v,
+                                       bool is_causal, float softmax_scale, bool bshd, bool out_fp32) {
+  check_common(q, k, v);
+  c10::cuda::CUDAGuard guard(q.device());
+  const int64_t d0 = q.size(0), d1 = q.size(1), d2 = q.size(2), D = q.size(3);
+  const int64_t B = d0, H = bshd ? d2 : d1, S = bshd ? d1 : d2;
+  TORCH_CHECK(D == 64 || D == 128, "head_dim must be 64 or 128, got ", D);
+  TORCH_CHECK(B >= 1 && H >= 1 && S >= 1, "empty tensors are not supported");
+
+  auto out = out_fp32 ? torch::empty(q.sizes(), q.options().dtype(at::kFloat)) : torch::empty_like(q);
+  auto lse = torch::empty({B, H, S}, q.options().dtype(at::kFloat));
+
+  tfa_fwd_args a;
+  a.q = q.data_ptr();
+  a.k = k.data_ptr();
+  a.v = v.data_ptr();
+  a.out = out.data_ptr();
+  a.lse = lse.data_ptr<float>();
+  a.B = static_cast<int32_t>(B);
+  a.H = static_cast<int32_t>(H);
+  a.S = static_cast<int32_t>(S);
+  a.D = static_cast<int32_t>(D);
+  if (bshd) {
+    a.stride_b = S * H * D; a.stride_s = H * D; a.stride_h = D;
+  } else {
+    a.stride_b = H * S * D; a.stride_h = S * D; a.stride_s = D;
+  }
+  a.dtype = q.scalar_type() == at::kBFloat16 ? TFA_BF16 : TFA_FP16;
+  a.is_causal = is_causal ? 1 : 0;
+  a.softmax_scale = softmax_scale;
+  a.out_fp32 = out_fp32 ? 1 : 0;
+  a.stream = at::cuda::getCurrentCUDAStream(q.device().index()).stream();
+  raise_on_error(tfa_fwd_ex(&a));
+  return {out, lse};
+}
+
+}  // namespace
+
+// The reference entry point (flash_attention.cu:741).  Positional-only, all five arguments
+// required -- exactly what the reference's pybind registration yields (attention_api.cpp:8).
+std::vector<torch::Tensor> flash_attention_v2_cutlass(torch::Tensor q, torch::Tensor k, torch::Tensor v,
+                                                      bool is_causal, float softmax_scale) {
+  TFA_CHECK_INPUT(q);
+  TFA_CHECK_INPUT(k);
+  TFA_CHECK_INPUT(v);
+  return fwd_generic(q, k, v, is_causal, softmax_scale, /*bshd=*/false, /*out_fp32=*/false);
+}
+
+// (B,S,H,D) layout of the official flash_attn package (test.py:71-75 transposes into it);
+// served by TMA strides, no transpose copy.
+std::vector<torch::Tensor> flash_attention_v2_bshd(torch::Tensor q, torch::Tensor k, torch::Tensor v, bool is_causal,
+                                                   float softmax_scale) {
+  TFA_CHECK_INPUT(q);
+  TFA_CHECK_INPUT(k);
+  TFA_CHECK_INPUT(v);
+  return fwd_generic(q, k, v, is_causal, softmax_scale, /*bshd=*/true, /*out_fp32=*/false);
+}
+
+// Validation build: identical kernel, epilogue skips the final 16-bit rounding (the idea of the
+// reference's standalone DEBUG build, standalone_src/flash_attention_cutlass_standalone.cu:18-23,685-689).
+std::vector<torch::Tensor> flash_attention_v2_fp32out(torch::Tensor q, torch::Tensor k, torch::Tensor v,
+                                                      bool is_causal, float softmax_scale) {
+  TFA_CHECK_INPUT(q);
+  TFA_CHECK_INPUT(k);
+  TFA_CHECK_INPUT(v);
+  return fwd_generic(q, k, v, is_causal, softmax_scale, /*bshd=*/false, /*out_fp32=*/true);
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("flash_attention_v2_cutlass", &flash_attention_v2_cutlass,
+        "Flash attention v2 forward, B200-native (sm_100a tcgen05/TMEM/TMA)");
+  // the name BASELINE.json's north_star uses for the same call
+  m.def("flash_attn_fwd", &flash_attention_v2_cutlass, "alias of flash_attention_v2_cutlass");
+  m.def("flash_attention_v2_bshd", &flash_attention_v2_bshd, "same op on (B,S,H,D) tensors");
+  m.def("flash_attention_v2_fp32out", &flash_attention_v2_fp32out, "same op, fp32 output (validation)");
+  m.def("launch_count", []() { return tfa_launch_count(); }, "kernels launched by the library so far");
+  m.def("abi_version", []() { return tfa_abi_version(); });
+}

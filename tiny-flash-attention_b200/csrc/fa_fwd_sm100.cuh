@@ -1,0 +1,418 @@
+// fa_fwd_sm100.cuh -- the fused attention-forward kernel for sm_100a (B200).
+//
+//   O = softmax(scale * Q K^T  [+ causal mask]) V ,  LSE = scale*max + ln(sum)
+//
+// One hand-written kernel replaces the reference's CuTe/sm80 kernel
+// (/root/reference/flash_attention_cutlass/csrc/flash_attention.cu:373-685).  The algorithm is
+// the same FA-2 recurrence; the machine mapping is Blackwell-first:
+//
+//   * one CTA = TWO 128-row Q tiles of one (batch, head) that share every K/V tile
+//     (reference: one 64-row tile per CTA, flash_attention.cu:695-699);
+//   * Q/K/V tiles are staged HBM -> shared memory by TMA (SWIZZLE_128B boxes of 64 x 128
+//     elements) behind mbarriers, a 4..6 deep K/V ring (reference: cp.async, single buffered,
+//     flash_attention.cu:521-525,556-565,581-590);
+//   * S = Q K^T and O += P V run on tcgen05 tensor cores with fp32 accumulators in TMEM:
+//     S is an SS-form UMMA (both operands K-major in smem), O is a TS-form UMMA whose A operand P
+//     is read from TMEM (it aliases S) and whose B operand is the V tile consumed in place as an
+//     MN-major operand -- no transpose, no ldmatrix.trans (reference: mma.sync m16n8k16 +
+//     ldmatrix(.trans), flash_attention.cu:84-132, kernel_traits.h:26-39);
+//   * softmax is one thread == one row (tcgen05.ld 32x32b): row max / row sum are thread-local,
+//     zero shuffles (reference: quad shfl.bfly reductions, utils.h:22-91); exp is ex2.approx with
+//     scale*log2(e) folded into one FFMA; O is rescaled lazily, only when the running max moved by
+//     more than 2^8 (reference: unconditional rescale every tile, flash_attention.cu:264-316);
+//   * the two Q tiles ping-pong: while softmax warpgroup 0 works on S0, the tensor core runs
+//     P1 V and the next Q1 K^T, and vice versa;
+//   * causal: KV tiles above the diagonal are skipped, only the diagonal tile is masked
+//     (reference: flash_attention.cu:536-540,576-578 with 64-wide tiles);
+//   * epilogue: O/l -> 16-bit -> swizzled smem staging -> coalesced 128-bit st.global.v4
+//     (reference: flash_attention.cu:608-663), LSE by the row-owner threads (:666-683).
+//
+// Warp roles (384 threads): warps 0-3 softmax/correction/epilogue for Q tile 0, warps 4-7 the same
+// for Q tile 1, warp 8 TMA producer (one lane), warp 9 TMEM allocator + UMMA issuer (one lane),
+// warps 10-11 idle (they exist so register re-allocation is warpgroup aligned).
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace tfa {
+
+struct FwdParams {
+  void* out;          // 16-bit output, element strides below
+  float* out_f32;     // fp32 output (validation build), same strides
+  float* lse;         // (BH, S) fp32 or nullptr
+  long long o_stride_b, o_stride_h, o_stride_s;  // elements
+  int H;
+  int S;
+  int npairs;         // ceil(S / 256)
+  float scale;        // softmax_scale
+  float scale_log2;   // softmax_scale * log2(e)
+  DebugRecord* dbg;
+};
+
+template <int D>
+struct FwdCfg {
+  static_assert(D == 64 || D == 128, "head_dim must be 64 or 128");
+  static constexpr int BM = 128;                    // rows per Q tile
+  static constexpr int BN = 128;                    // keys per KV tile
+  static constexpr int SLABS = D / 64;              // 128-byte-wide swizzle slabs per tile row
+  static constexpr int SLAB_BYTES = 128 * 128;      // 128 rows x 128 B
+  static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
+  static constexpr int NSTAGE = (D == 128) ? 4 : 8; // K/V ring depth (tiles)
+  static constexpr int NUM_BARS = 2 + 2 * NSTAGE + 2 + 2 + 2;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + 2 * TILE_BYTES + NSTAGE * TILE_BYTES + NUM_BARS * 8 + 16;
+  // TMEM columns (fp32): S0 | S1 | O0 | O1 ; P_t aliases the first 64 columns of S_t
+  static constexpr int TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 256 + D;
+  static constexpr int TM_COLS = 512;
+  static constexpr int THREADS = 384;
+};
+
+// watchdog call sites
+enum : uint32_t {
+  SITE_LOAD_EMPTY = 1, SITE_MMA_K0 = 2, SITE_MMA_Q = 3, SITE_MMA_V = 4, SITE_MMA_P = 5, SITE_MMA_K = 6,
+  SITE_SM_S = 7, SITE_EPI_O = 8
+};
+
+constexpr float kRescaleThresholdLog2 = 8.0f;
+// register re-allocation after the prologue: 2 softmax warpgroups x 224 + 1 service warpgroup x 64 = 512 x 128
+constexpr uint32_t kRegsSoftmax = 224;
+constexpr uint32_t kRegsOther = 64;  // lazy rescale: tolerate P up to 2^8
+
+template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
+__global__ void __launch_bounds__(384, 1)
+fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+  using C = FwdCfg<D>;
+  constexpr int TILE = C::TILE_BYTES;
+  constexpr int NSTAGE = C::NSTAGE;
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte alignment (the swizzle is a function of address bits 7..9)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                       // 2 tiles
+  uint8_t* sKV = smem + 2 * TILE;           // NSTAGE tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NSTAGE * TILE);
+  uint64_t* q_full = bars;                  // [2]
+  uint64_t* kv_full = bars + 2;             // [NSTAGE]
+  uint64_t* kv_empty = kv_full + NSTAGE;    // [NSTAGE]
+  uint64_t* s_full = kv_empty + NSTAGE;     // [2]
+  uint64_t* p_full = s_full + 2;            // [2]
+  uint64_t* o_full = p_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- work decode: (b,h) major, heaviest (largest pair index) first inside a head ----
+  const int bh = blockIdx.x / p.npairs;
+  const int pr = p.npairs - 1 - (blockIdx.x % p.npairs);
+  const int bidx = bh / p.H, hidx = bh % p.H;
+  const int S = p.S;
+  const int nkv_total = (S + C::BN - 1) / C::BN;
+  int row0[2], nblk[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    row0[t] = pr * 256 + t * 128;
+    const bool active = row0[t] < S;
+    nblk[t] = active ? (CAUSAL ? min(nkv_total, row0[t] / C::BN + 1) : nkv_total) : 0;
+  }
+  const int nmax = max(nblk[0], nblk[1]);
+
+  // ---- one-time setup ----
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&o_full[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, C::TM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // =========================== TMA producer ===========================
+    setmaxnreg_dec<kRegsOther>();
+    if (lane == 0) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (nblk[t] > 0) {
+          mbar_arrive_expect_tx(&q_full[t], TILE);
+#pragma unroll
+          for (int sl = 0; sl < C::SLABS; ++sl)
+            tma_load_4d(sQ + t * TILE + sl * C::SLAB_BYTES, &tmQ, &q_full[t], sl * 64, row0[t], hidx, bidx);
+        }
+      }
+      int it = 0;
+      for (int j = 0; j < nmax; ++j) {
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv, ++it) {
+          const int slot = it % NSTAGE;
+          const uint32_t par = (it / NSTAGE) & 1;
+          mbar_wait(&kv_empty[slot], par ^ 1, p.dbg, SITE_LOAD_EMPTY, it);
+          mbar_arrive_expect_tx(&kv_full[slot], TILE);
+          const CUtensorMap* tm = (kv == 0) ? &tmK : &tmV;
+#pragma unroll
+          for (int sl = 0; sl < C::SLABS; ++sl)
+            tma_load_4d(sKV + slot * TILE + sl * C::SLAB_BYTES, tm, &kv_full[slot], sl * 64, j * C::BN, hidx, bidx);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // =========================== UMMA issuer ===========================
+    setmaxnreg_dec<kRegsOther>();
+    if (lane == 0) {
+      constexpr uint32_t FMT = IS_BF16 ? 1u : 0u;
+      const uint32_t idescS = umma_idesc_f16(FMT, 128, 128, 0, 0);  // A,B K-major
+      const uint32_t idescO = umma_idesc_f16(FMT, 128, D, 0, 1);    // B (=V) MN-major
+      const uint32_t sQ_addr = smem_u32(sQ);
+      const uint32_t sKV_addr = smem_u32(sKV);
+
+      auto issue_S = [&](int t, uint32_t k_addr) {
+        const uint32_t d_tmem = tmem_base + (t == 0 ? C::TM_S0 : C::TM_S1);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k / 4) * C::SLAB_BYTES + (k % 4) * 32;
+          const uint64_t a = umma_smem_desc(sQ_addr + t * TILE + off, 16, 1024);
+          const uint64_t b = umma_smem_desc(k_addr + off, 16, 1024);
+          umma_ss(d_tmem, a, b, idescS, k > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_PV = [&](int t, uint32_t v_addr, bool acc) {
+        const uint32_t d_tmem = tmem_base + (t == 0 ? C::TM_O0 : C::TM_O1);
+        const uint32_t p_tmem = tmem_base + (t == 0 ? C::TM_S0 : C::TM_S1);
+#pragma unroll
+        for (int k = 0; k < C::BN / 16; ++k) {
+          // 16 kv rows per step = 2048 B; LBO = next 64-column slab, SBO = next 8-row group
+          const uint64_t b = umma_smem_desc(v_addr + k * 2048, C::SLAB_BYTES, 1024);
+          umma_ts(d_tmem, p_tmem + k * 8, b, idescO, (acc || k > 0) ? 1u : 0u);
+        }
+      };
+
+      // prologue: S_t(0) = Q_t K_0^T
+      mbar_wait(&kv_full[0], 0, p.dbg, SITE_MMA_K0, 0);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (nblk[t] > 0) {
+          mbar_wait(&q_full[t], 0, p.dbg, SITE_MMA_Q, t);
+          tc_fence_after();
+          issue_S(t, sKV_addr);
+          umma_commit(&s_full[t]);
+        }
+      }
+      umma_commit(&kv_empty[0]);
+
+      for (int j = 0; j < nmax; ++j) {
+        const int v_it = 2 * j + 1, k_it = 2 * j + 2;
+        const int vslot = v_it % NSTAGE, kslot = k_it % NSTAGE;
+        const uint32_t vpar = (v_it / NSTAGE) & 1, kpar = (k_it / NSTAGE) & 1;
+        mbar_wait(&kv_full[vslot], vpar, p.dbg, SITE_MMA_V, j);
+        bool k_ready = false;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (j >= nblk[t]) continue;
+          mbar_wait(&p_full[t], j & 1, p.dbg, SITE_MMA_P, j * 2 + t);
+          tc_fence_after();
+          issue_PV(t, sKV_addr + vslot * TILE, j > 0);
+          if (!(t == 0 && j < nblk[1])) umma_commit(&kv_empty[vslot]);   // last user of V_j
+          if (j + 1 < nblk[t]) {
+            if (!k_ready) {
+              mbar_wait(&kv_full[kslot], kpar, p.dbg, SITE_MMA_K, j);
+              tc_fence_after();
+              k_ready = true;
+            }
+            issue_S(t, sKV_addr + kslot * TILE);
+            umma_commit(&s_full[t]);      // also covers PV_t(j): O_t is quiescent when S_t(j+1) lands
+            if (!(t == 0 && j + 1 < nblk[1])) umma_commit(&kv_empty[kslot]);  // last user of K_{j+1}
+          } else {
+            umma_commit(&o_full[t]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 8) {
+    // ================= softmax / correction / epilogue warpgroup t =================
+    setmaxnreg_inc<kRegsSoftmax>();
+    const int t = warp >> 2;
+    const int n = (t == 0) ? nblk[0] : nblk[1];
+    const int trow0 = (t == 0) ? row0[0] : row0[1];
+    if (n > 0) {
+      const int r = threadIdx.x & 127;                       // row inside the Q tile == TMEM lane
+      const int row_g = trow0 + r;                            // global query row
+      const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+      const uint32_t tS = tmem_base + lane_base + (t == 0 ? C::TM_S0 : C::TM_S1);
+      const uint32_t tO = tmem_base + lane_base + (t == 0 ? C::TM_O0 : C::TM_O1);
+      const float c = p.scale_log2;
+
+      float m_ref = 0.f;   // reference max the exponentials are taken against (raw score units)
+      float l = 0.f;       // running sum of exp2((s - m_ref) * c)
+
+      for (int j = 0; j < n; ++j) {
+        mbar_wait(&s_full[t], j & 1, p.dbg, SITE_SM_S, j * 2 + t);
+        tc_fence_after();
+
+        uint32_t sr[128];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) tmem_ld_x32(tS + q4 * 32, &sr[q4 * 32]);
+        tmem_wait_ld();
+
+        // ---- mask: keys beyond S, and (diagonal tile) keys after the query ----
+        const int col0 = j * C::BN;
+        int lim = S - col0;                                  // valid keys in this tile
+        if (CAUSAL) lim = min(lim, row_g - col0 + 1);
+        if (lim < C::BN) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= lim) sr[i] = 0xff800000u;               // -inf
+        }
+
+        // ---- row max (thread-local) ----
+        float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]);
+        float mx2 = __uint_as_float(sr[2]), mx3 = __uint_as_float(sr[3]);
+#pragma unroll
+        for (int i = 4; i < 128; i += 8) {
+          mx0 = fmax3(mx0, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
+          if (i + 4 < 128) {
+            mx2 = fmax3(mx2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
+            mx3 = fmax3(mx3, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
+          }
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+
+        // ---- lazy rescale of l and O (only when the max moved by more than 2^8) ----
+        if (j == 0) {
+          m_ref = mx;      // always finite: key 0 is visible to every row
+        } else {
+          const bool need = (mx - m_ref) * c > kRescaleThresholdLog2;
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = need ? mx : m_ref;
+            const float alpha = ex2_approx((m_ref - m_new) * c);   // == 1 when !need
+            m_ref = m_new;
+            l *= alpha;
+            // PV_t(j-1) has completed (s_full covers it) and PV_t(j) waits for p_full: O_t is ours.
+#pragma unroll
+            for (int ch = 0; ch < D / 32; ++ch) {
+              uint32_t o[32];
+              tmem_ld_x32(tO + ch * 32, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x32(tO + ch * 32, o);
+            }
+          }
+        }
+
+        // ---- P = exp2(s*c - m_ref*c); l += rowsum(P) (fp32, before rounding); pack to 16 bit ----
+        const float neg_mc = -m_ref * c;
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(sr[h * 64 + 2 * i + 0]), c, neg_mc));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(sr[h * 64 + 2 * i + 1]), c, neg_mc));
+            const float e2 = ex2_approx(fmaf(__uint_as_float(sr[h * 64 + 2 * i + 2]), c, neg_mc));
+            const float e3 = ex2_approx(fmaf(__uint_as_float(sr[h * 64 + 2 * i + 3]), c, neg_mc));
+            sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
+            pk[i] = pack_16x2<IS_BF16>(e0, e1);
+            pk[i + 1] = pack_16x2<IS_BF16>(e2, e3);
+          }
+          tmem_st_x32(tS + h * 32, pk);     // P aliases columns [0,64) of S
+        }
+        l += (sum0 + sum1) + (sum2 + sum3);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+      }
+
+      // ---------------------------- epilogue ----------------------------
+      mbar_wait(&o_full[t], 0, p.dbg, SITE_EPI_O, t);
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+      const long long tile_off = static_cast<long long>(bidx) * p.o_stride_b + static_cast<long long>(hidx) * p.o_stride_h;
+
+      if (p.lse != nullptr && row_g < S)
+        p.lse[static_cast<long long>(bh) * S + row_g] = m_ref * p.scale + logf(l);
+
+      if constexpr (OUT_F32) {
+        float* orow = p.out_f32 + tile_off + static_cast<long long>(row_g) * p.o_stride_s;
+#pragma unroll
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld_x32(tO + ch * 32, o);
+          tmem_wait_ld();
+          if (row_g < S) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 v4 = make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
+                                      __uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+              *reinterpret_cast<float4*>(orow + ch * 32 + i) = v4;
+            }
+          }
+        }
+      } else {
+        // registers -> swizzled staging (re-uses this tile's Q buffer: Q_t is dead once o_full fired)
+        uint8_t* stg = sQ + t * TILE;
+        constexpr int ROW_BYTES = D * 2;
+        constexpr int CHUNKS = ROW_BYTES / 16;               // 16-byte chunks per row
+#pragma unroll
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld_x32(tO + ch * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 v4;
+            v4.x = pack_16x2<IS_BF16>(__uint_as_float(o[q * 8 + 0]) * inv_l, __uint_as_float(o[q * 8 + 1]) * inv_l);
+            v4.y = pack_16x2<IS_BF16>(__uint_as_float(o[q * 8 + 2]) * inv_l, __uint_as_float(o[q * 8 + 3]) * inv_l);
+            v4.z = pack_16x2<IS_BF16>(__uint_as_float(o[q * 8 + 4]) * inv_l, __uint_as_float(o[q * 8 + 5]) * inv_l);
+            v4.w = pack_16x2<IS_BF16>(__uint_as_float(o[q * 8 + 6]) * inv_l, __uint_as_float(o[q * 8 + 7]) * inv_l);
+            const int chunk = ch * 4 + q;
+            const int phys = (chunk & ~7) | ((chunk ^ r) & 7);
+            *reinterpret_cast<uint4*>(stg + r * ROW_BYTES + phys * 16) = v4;
+          }
+        }
+        named_bar_sync(1 + t, 128);
+        // coalesced 128-bit stores: consecutive threads write consecutive 16-byte chunks of a row
+        uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + tile_off * 2;
+#pragma unroll 4
+        for (int idx = r; idx < 128 * CHUNKS; idx += 128) {
+          const int rr = idx / CHUNKS, chunk = idx % CHUNKS;
+          const int phys = (chunk & ~7) | ((chunk ^ rr) & 7);
+          const uint4 v4 = *reinterpret_cast<const uint4*>(stg + rr * ROW_BYTES + phys * 16);
+          const int rg = trow0 + rr;
+          if (rg < S) st_global_v4(obase + static_cast<long long>(rg) * p.o_stride_s * 2 + chunk * 16, v4);
+        }
+      }
+      tc_fence_before();
+    }
+  } else {
+    setmaxnreg_dec<kRegsOther>();   // warps 10-11: idle, give their registers away
+  }
+
+  // ---- teardown ----
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TM_COLS);
+  }
+}
+
+}  // namespace tfa

@@ -1,0 +1,312 @@
+// tfa_api.cu -- host side of the C ABI declared in include/tfa_b200.h.
+//
+// Replaces the reference's host dispatch chain
+//   flash_attention_v2_cutlass -> set_params_fprop -> run_flash_attn_cutlass ->
+//   FP16_SWITCH -> FWD_HEADDIM_SWITCH -> BOOL_SWITCH -> run_flash_fwd
+// (/root/reference/flash_attention_cutlass/csrc/flash_attention.cu:320-361,687-772,
+//  csrc/static_switch.h:17-66) for the sm_100a kernel in fa_fwd_sm100.cuh.
+// Differences on purpose: arguments are validated and rejected loudly, the
+// caller's stream is honoured, nothing synchronises the device, nothing calls exit().
+#include "../../include/tfa_b200.h"
+#include "fa_fwd_sm100.cuh"
+
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <atomic>
+#include <mutex>
+#include <vector>
+#include <cstring>
+
+namespace {
+
+using tfa::DebugRecord;
+using tfa::FwdCfg;
+using tfa::FwdParams;
+
+std::atomic<unsigned long long> g_launches{0};
+
+// ---- driver entry point for cuTensorMapEncodeTiled (no link-time libcuda dependency) ----
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+// ---- host-mapped watchdog record ----
+DebugRecord* g_dbg_host = nullptr;
+DebugRecord* g_dbg_dev = nullptr;
+std::once_flag g_dbg_once;
+void init_dbg() {
+  std::call_once(g_dbg_once, [] {
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, sizeof(DebugRecord), cudaHostAllocMapped) == cudaSuccess) {
+      std::memset(h, 0, sizeof(DebugRecord));
+      void* d = nullptr;
+      if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+        g_dbg_host = static_cast<DebugRecord*>(h);
+        g_dbg_dev = static_cast<DebugRecord*>(d);
+      }
+    }
+  });
+}
+
+// (B?,H?,S,D)-strided 16-bit tensor -> 4-D tiled map with dims (D, S, H, B); the kernel addresses it as
+// (x = head-dim offset, y = sequence row, z = head, w = batch).  Box = 64 x 128 elements, SWIZZLE_128B.
+int make_tmap(CUtensorMap* m, const void* base, int dtype, int D, int S, int B, int H, long long sb,
+              long long sh, long long ss) {
+  auto encode = get_encode_fn();
+  if (!encode) return TFA_EDRIVER;
+  const CUtensorMapDataType dt = (dtype == TFA_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const cuuint32_t box[4] = {64, 128, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(H),
+                              static_cast<cuuint64_t>(B)};
+  // size-1 dims may carry any stride; give them a legal one
+  const cuuint64_t s1 = static_cast<cuuint64_t>(ss) * 2;
+  const cuuint64_t s2 = (H > 1 ? static_cast<cuuint64_t>(sh) : static_cast<cuuint64_t>(ss) * S) * 2;
+  const cuuint64_t s3 = (B > 1 ? static_cast<cuuint64_t>(sb) : s2 / 2 * H) * 2;
+  const cuuint64_t strides[3] = {s1, s2, s3};
+  for (int i = 0; i < 3; ++i)
+    if ((strides[i] % 16) || strides[i] >= (1ull << 40)) return TFA_EINVAL_STRIDE;
+  CUresult r = encode(m, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : TFA_EDRIVER;
+}
+
+template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
+int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FwdParams& p, int nblocks,
+                cudaStream_t stream) {
+  using C = FwdCfg<D>;
+  auto kern = tfa::fa_fwd_sm100_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
+  kern<<<nblocks, C::THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <int D>
+int dispatch(bool causal, bool bf16, bool f32, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+             const FwdParams& p, int nblocks, cudaStream_t s) {
+#define TFA_GO(C_, B_, F_) return launch_inst<D, C_, B_, F_>(tq, tk, tv, p, nblocks, s)
+  if (causal) {
+    if (bf16) { if (f32) TFA_GO(true, true, true); else TFA_GO(true, true, false); }
+    else      { if (f32) TFA_GO(true, false, true); else TFA_GO(true, false, false); }
+  } else {
+    if (bf16) { if (f32) TFA_GO(false, true, true); else TFA_GO(false, true, false); }
+    else      { if (f32) TFA_GO(false, false, true); else TFA_GO(false, false, false); }
+  }
+#undef TFA_GO
+}
+
+bool arch_ok() {
+  static int ok = [] {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+  }();
+  return ok != 0;
+}
+
+int fwd_impl(const tfa_fwd_args& a) {
+  if (!a.q || !a.k || !a.v || !a.out) return TFA_EINVAL_PTR;
+  if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) |
+       reinterpret_cast<uintptr_t>(a.out)) & 15u)
+    return TFA_EINVAL_PTR;
+  if (a.D != 64 && a.D != 128) return TFA_EINVAL_DIM;
+  if (a.B < 1 || a.H < 1 || a.S < 1) return TFA_EINVAL_SHAPE;
+  if (a.dtype != TFA_BF16 && a.dtype != TFA_FP16) return TFA_EINVAL_DTYPE;
+  if (a.stride_s < a.D || (a.stride_s % 8) || (a.stride_h % 8) || (a.stride_b % 8)) return TFA_EINVAL_STRIDE;
+  if (!arch_ok()) return TFA_EARCH;
+  init_dbg();
+
+  const long long npairs = (static_cast<long long>(a.S) + 255) / 256;
+  cudaStream_t stream = static_cast<cudaStream_t>(a.stream);
+
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap(&tq, a.q, a.dtype, a.D, a.S, a.B, a.H, a.stride_b, a.stride_h, a.stride_s))) return rc;
+  if ((rc = make_tmap(&tk, a.k, a.dtype, a.D, a.S, a.B, a.H, a.stride_b, a.stride_h, a.stride_s))) return rc;
+  if ((rc = make_tmap(&tv, a.v, a.dtype, a.D, a.S, a.B, a.H, a.stride_b, a.stride_h, a.stride_s))) return rc;
+
+  FwdParams p;
+  p.out = a.out_fp32 ? nullptr : a.out;
+  p.out_f32 = a.out_fp32 ? static_cast<float*>(a.out) : nullptr;
+  p.lse = a.lse;
+  p.o_stride_b = a.stride_b;
+  p.o_stride_h = a.stride_h;
+  p.o_stride_s = a.stride_s;
+  p.H = a.H;
+  p.S = a.S;
+  p.npairs = static_cast<int>(npairs);
+  p.scale = a.softmax_scale;
+  p.scale_log2 = a.softmax_scale * 1.4426950408889634f;
+  p.dbg = g_dbg_dev;
+
+  const long long nblocks = npairs * a.B * a.H;
+  if (nblocks > 0x7fffffffLL) return TFA_EINVAL_SHAPE;
+  const bool causal = a.is_causal != 0, bf16 = a.dtype == TFA_BF16, f32 = a.out_fp32 != 0;
+  if (a.D == 64) rc = dispatch<64>(causal, bf16, f32, tq, tk, tv, p, static_cast<int>(nblocks), stream);
+  else           rc = dispatch<128>(causal, bf16, f32, tq, tk, tv, p, static_cast<int>(nblocks), stream);
+  if (rc) return rc;
+  return 0;
+}
+
+// ---- host-buffer path workspace ----
+struct HostWs {
+  void* d[4] = {nullptr, nullptr, nullptr, nullptr};   // q k v o
+  float* dlse = nullptr;
+  size_t bytes = 0, lse_bytes = 0;
+  std::vector<cudaStream_t> streams;
+  std::vector<cudaEvent_t> events;
+} g_ws;
+std::mutex g_ws_mu;
+
+void ws_release_locked() {
+  for (auto& p : g_ws.d) { if (p) cudaFree(p); p = nullptr; }
+  if (g_ws.dlse) cudaFree(g_ws.dlse);
+  g_ws.dlse = nullptr;
+  g_ws.bytes = g_ws.lse_bytes = 0;
+  for (auto s : g_ws.streams) cudaStreamDestroy(s);
+  g_ws.streams.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfa_abi_version(void) { return TFA_ABI_VERSION; }
+
+int tfa_fwd_ex(const tfa_fwd_args* args) {
+  if (!args) return TFA_EINVAL_PTR;
+  return fwd_impl(*args);
+}
+
+int tfa_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int S, int D, int dtype,
+            int is_causal, float softmax_scale, void* cuda_stream) {
+  tfa_fwd_args a;
+  std::memset(&a, 0, sizeof(a));
+  a.q = q; a.k = k; a.v = v; a.out = out; a.lse = lse;
+  a.B = B; a.H = H; a.S = S; a.D = D;
+  a.stride_s = D;
+  a.stride_h = static_cast<long long>(S) * D;
+  a.stride_b = static_cast<long long>(H) * S * D;
+  a.dtype = dtype;
+  a.is_causal = is_causal;
+  a.softmax_scale = softmax_scale;
+  a.out_fp32 = 0;
+  a.stream = cuda_stream;
+  return fwd_impl(a);
+}
+
+int tfa_fwd_host(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int S, int D,
+                 int dtype, int is_causal, float softmax_scale, int n_chunks) {
+  if (!q || !k || !v || !out) return TFA_EINVAL_PTR;
+  if (D != 64 && D != 128) return TFA_EINVAL_DIM;
+  if (B < 1 || H < 1 || S < 1) return TFA_EINVAL_SHAPE;
+  if (dtype != TFA_BF16 && dtype != TFA_FP16) return TFA_EINVAL_DTYPE;
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  const long long BH = static_cast<long long>(B) * H;
+  const size_t head_bytes = static_cast<size_t>(S) * D * 2;
+  const size_t total = head_bytes * BH;
+  const size_t lse_total = static_cast<size_t>(BH) * S * sizeof(float);
+  cudaError_t e;
+  if (g_ws.bytes < total) {
+    for (auto& p : g_ws.d) { if (p) cudaFree(p); p = nullptr; }
+    g_ws.bytes = 0;
+    for (auto& p : g_ws.d)
+      if ((e = cudaMalloc(&p, total)) != cudaSuccess) { ws_release_locked(); return static_cast<int>(e); }
+    g_ws.bytes = total;
+  }
+  if (g_ws.lse_bytes < lse_total) {
+    if (g_ws.dlse) cudaFree(g_ws.dlse);
+    g_ws.dlse = nullptr; g_ws.lse_bytes = 0;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&g_ws.dlse), lse_total)) != cudaSuccess) return static_cast<int>(e);
+    g_ws.lse_bytes = lse_total;
+  }
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > BH) n_chunks = static_cast<int>(BH);
+  const int nstreams = n_chunks < 4 ? n_chunks : 4;
+  while (static_cast<int>(g_ws.streams.size()) < nstreams) {
+    cudaStream_t s;
+    if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) return static_cast<int>(e);
+    g_ws.streams.push_back(s);
+  }
+  // chunk over flattened (batch*head): every head is an independent problem
+  int rc = 0;
+  for (int c = 0; c < n_chunks && rc == 0; ++c) {
+    const long long h0 = BH * c / n_chunks, h1 = BH * (c + 1) / n_chunks;
+    const long long nh = h1 - h0;
+    if (nh <= 0) continue;
+    cudaStream_t s = g_ws.streams[c % nstreams];
+    const size_t off = head_bytes * h0, nbytes = head_bytes * nh;
+    const void* src[3] = {q, k, v};
+    for (int i = 0; i < 3; ++i)
+      if ((e = cudaMemcpyAsync(static_cast<char*>(g_ws.d[i]) + off, static_cast<const char*>(src[i]) + off, nbytes,
+                               cudaMemcpyHostToDevice, s)) != cudaSuccess) { rc = static_cast<int>(e); break; }
+    if (rc) break;
+    rc = tfa_fwd(static_cast<char*>(g_ws.d[0]) + off, static_cast<char*>(g_ws.d[1]) + off,
+                 static_cast<char*>(g_ws.d[2]) + off, static_cast<char*>(g_ws.d[3]) + off,
+                 lse ? g_ws.dlse + h0 * S : nullptr, 1, static_cast<int>(nh), S, D, dtype, is_causal, softmax_scale, s);
+    if (rc) break;
+    if ((e = cudaMemcpyAsync(static_cast<char*>(out) + off, static_cast<char*>(g_ws.d[3]) + off, nbytes,
+                             cudaMemcpyDeviceToHost, s)) != cudaSuccess) { rc = static_cast<int>(e); break; }
+    if (lse && (e = cudaMemcpyAsync(lse + h0 * S, g_ws.dlse + h0 * S, static_cast<size_t>(nh) * S * sizeof(float),
+                                    cudaMemcpyDeviceToHost, s)) != cudaSuccess) { rc = static_cast<int>(e); break; }
+  }
+  for (int i = 0; i < nstreams; ++i) {
+    e = cudaStreamSynchronize(g_ws.streams[i]);
+    if (e != cudaSuccess && rc == 0) rc = static_cast<int>(e);
+  }
+  if (rc != 0 && g_dbg_host && g_dbg_host->flag) rc = TFA_EDEVICE_FAULT;
+  return rc;
+}
+
+void tfa_host_release(void) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  ws_release_locked();
+}
+
+unsigned long long tfa_launch_count(void) { return g_launches.load(); }
+// exported for the self tests living in another translation unit
+void tfa_internal_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void* tfa_internal_dbg_dev(void) { init_dbg(); return g_dbg_dev; }
+void* tfa_internal_encode_fn(void) { return reinterpret_cast<void*>(get_encode_fn()); }
+
+int tfa_debug_record(unsigned int out[8]) {
+  if (!out) return TFA_EINVAL_PTR;
+  if (!g_dbg_host) { std::memset(out, 0, 8 * sizeof(unsigned int)); return 0; }
+  std::memcpy(out, g_dbg_host, 8 * sizeof(unsigned int));
+  return 0;
+}
+void tfa_debug_clear(void) {
+  if (g_dbg_host) std::memset(g_dbg_host, 0, sizeof(DebugRecord));
+}
+
+const char* tfa_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case TFA_EINVAL_PTR: return "tfa: null or misaligned (16 B) pointer";
+    case TFA_EINVAL_DIM: return "tfa: head_dim must be 64 or 128";
+    case TFA_EINVAL_SHAPE: return "tfa: B, H, S must be >= 1 (and B*H*ceil(S/256) < 2^31)";
+    case TFA_EINVAL_DTYPE: return "tfa: dtype must be TFA_BF16 (0) or TFA_FP16 (1)";
+    case TFA_EINVAL_STRIDE: return "tfa: strides must be multiples of 8 elements with unit head_dim stride";
+    case TFA_EDRIVER: return "tfa: cuTensorMapEncodeTiled unavailable or failed";
+    case TFA_EARCH: return "tfa: this library only runs on compute capability 10.x (B200, sm_100a)";
+    case TFA_EDEVICE_FAULT: return "tfa: kernel watchdog fired (see tfa_debug_record)";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "tfa: unknown error";
+  }
+}
+
+}  // extern "C"
