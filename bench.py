@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- attention-forward TFLOP/s on B200 (the one hot path), per the driver contract.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[4], the configuration the metric's "1/2/4/8 B200"
+clause is quoted on -- B=64 H=32 S=4096 D=128 bf16 causal, sharded over (B*H).  It fits one GPU
+(Q,K,V,O = 8.6 GB), so N=1 runs ALL of it and N>1 splits the batch: total work fixed => "strong" scaling.
+A step = one forward pass over the whole job: every rank runs the sm_100a kernel on its B/N batches and,
+for N>1, the O shards are all-gathered (NCCL) so every rank ends the step holding the full O.
+
+Printed JSON (rank 0, one line):
+  value        whole-job TFLOP/s, F = 2*B*H*S^2*D (BASELINE.json's "effective FLOPs"; equals the usual
+               causal count 4*B*H*S^2*D/2), inputs resident in HBM, CUDA-event time, max over ranks.
+  e2e          the same metric through the C ABI host-buffer call tfa_fwd_host(): pinned HOST q/k/v in,
+               HOST out/lse back, copies inside the timed region.
+  roofline     tensor-core bound: achieved = F_per_launch / mean kernel time (CUDA events on the launch
+               stream, measured live here), peak = MEASURED_PEAKS.json bf16_tflops (burst).
+  cpu_baseline the reference's own C++ CPU attention (oracle/_ref, compiled unmodified) timed on this box's
+               host cores on a bounded head-sample of the same workload (rank 0, N=1 only).
+  configs      BASELINE.json configs[1..3] timed the same way (N=1 only), for the headline table.
+`--impl reference` times only that CPU path (all host threads) on the same config/metric/unit.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "tiny-flash-attention_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOAD = {"name": "cfg5: B=64 H=32 S=4096 D=128 bf16 causal, sharded over (B*H)", "B": 64, "H": 32, "S": 4096,
+            "D": 128, "causal": True}
+EXTRA_CONFIGS = {
+    "cfg2: B=4 H=16 S=2048 D=64 bf16 non-causal": (4, 16, 2048, 64, False),
+    "cfg3: B=4 H=32 S=4096 D=128 bf16 causal": (4, 32, 4096, 128, True),
+    "cfg4: B=1 H=32 S=16384 D=128 bf16 causal": (1, 32, 16384, 128, True),
+}
+FALLBACK_PEAK_TFLOPS = 1590.0   # /opt/skills/guides/B200_PROFILING.md fallback
+METRIC = "attention TFLOPs/s (bf16, seqlen x head_dim) at 1/2/4/8 B200 vs roofline"
+
+
+def flops_effective(B, H, S, D):
+    return 2.0 * B * H * S * S * D
+
+
+def flops_std(B, H, S, D, causal):
+    return 4.0 * B * H * S * S * D * (0.5 if causal else 1.0)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return FALLBACK_PEAK_TFLOPS, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons DURING the timed region (NVML), as the profiling recipe asks."""
+
+    def __init__(self, index=0, period=0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU attention on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_reference_runner():
+    """Returns (fn(q,k,v,causal,scale)->out, kind, cores). Prefers oracle/_ref (the reference's C++ compiled
+    unmodified); falls back to the C oracle port of the same row-wise algorithm."""
+    from oracle import oracle as orc
+    import torch
+
+    cores = os.cpu_count() or 1
+    ker = orc.load_ref_kernels()
+    if ker is not None:
+        torch.set_num_threads(cores)
+        return (lambda q, k, v, c, s: ker.flash_attn(q, k, v, c, s)), "reference", cores
+    return (lambda q, k, v, c, s: torch.from_numpy(orc.rowwise_online(q.numpy(), k.numpy(), v.numpy(), c, s))), \
+        "port", orc.num_threads()
+
+
+def time_cpu_sample(fn, heads, S, D, causal, scale, steps, warmup, seed=20):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    q, k, v = (torch.empty(1, heads, S, D).normal_(0, 0.5, generator=g).to(torch.bfloat16).float() for _ in range(3))
+    for _ in range(warmup):
+        fn(q, k, v, causal, scale)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        fn(q, k, v, causal, scale)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def pick_sample_heads(fn, S, D, causal, scale, target_s, max_heads):
+    t = time_cpu_sample(fn, 2, S, D, causal, scale, 1, 0)[0] / 2.0        # seconds per head (also a warm-up)
+    return max(1, min(max_heads, int(target_s / max(t, 1e-6)))), t
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W = WORKLOAD
+    scale = 1.0 / math.sqrt(W["D"])
+    fn, kind, cores = cpu_reference_runner()
+    heads, per_head = pick_sample_heads(fn, W["S"], W["D"], W["causal"], scale, target_s=3.0,
+                                        max_heads=W["B"] * W["H"])
+    ts = time_cpu_sample(fn, heads, W["S"], W["D"], W["causal"], scale, args.steps, args.warmup)
+    total = sum(ts)
+    F = flops_effective(1, heads, W["S"], W["D"])
+    val = F * len(ts) / total / 1e12
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(ts) * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic N(0,0.5^2), seed 20",
+        "config": {"workload": W["name"], "B": W["B"], "H": W["H"], "S": W["S"], "D": W["D"], "causal": W["causal"],
+                   "step": f"bounded sample: {heads} of {W['B'] * W['H']} (batch*head) problems per step"},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": kind,
+                         "sample": f"{heads} heads x S{W['S']} x D{W['D']} causal fp32 per step, "
+                                   f"/root/reference/flash_attention_c flash_attn (OpenMP, all host threads)"},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def make_inputs(B, H, S, D, seed, device, dtype):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    return [torch.empty(B, H, S, D, dtype=dtype, device=device).normal_(0.0, 0.5, generator=g) for _ in range(3)]
+
+
+def time_kernel(tfa, q, k, v, causal, scale, out, lse, reps, warm, flush=None):
+    """Mean/median device time of the kernel alone (CUDA events on the launch stream)."""
+    import torch
+    for _ in range(warm):
+        tfa.fwd(q, k, v, causal, scale, out=out, lse=lse)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tfa.fwd(q, k, v, causal, scale, out=out, lse=lse)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    ts.sort()
+    return sum(ts) / len(ts), ts[len(ts) // 2], ts[0]
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import tfa_ctypes as tfa
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    tfa.lib()                                     # fail loudly if the CUDA library is missing
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    W = WORKLOAD
+    B, H, S, D, causal = W["B"], W["H"], W["S"], W["D"], W["causal"]
+    scale = 1.0 / math.sqrt(D)
+    from sharded import shard_batch
+    lo, hi = shard_batch(B, rank, world)
+    Bl = hi - lo
+    q, k, v = make_inputs(Bl, H, S, D, 20 + rank, dev, torch.bfloat16)
+    out = torch.empty_like(q)
+    lse = torch.empty(Bl, H, S, dtype=torch.float32, device=dev)
+    o_full = torch.empty(B, H, S, D, dtype=torch.bfloat16, device=dev) if world > 1 else None
+    peak, peak_sus, peak_src = load_peaks()
+
+    def step():
+        tfa.fwd(q, k, v, causal, scale, out=out, lse=lse)
+        if world > 1:
+            dist.all_gather_into_tensor(o_full, out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: K timed steps, device time, max over ranks ----
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    n0 = tfa.launch_count()
+    with ClockSampler(local_rank) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    launches = tfa.launch_count() - n0
+    t_total = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_total = float(tt.item())
+    t_step = t_total / args.steps
+    F_job = flops_effective(B, H, S, D)
+    value = F_job / t_step / 1e12
+
+    # ---- roofline: the kernel alone on this rank's shard ----
+    k_mean, k_med, k_min = time_kernel(tfa, q, k, v, causal, scale, out, lse, reps=max(args.steps, 5), warm=2)
+    F_launch = flops_effective(Bl, H, S, D)
+    achieved = F_launch / k_mean / 1e12
+    compute_only_value = achieved * world       # all ranks run the same-size shard concurrently
+
+    # ---- e2e: host buffers through the C ABI ----
+    e2e = None
+    if not args.no_e2e:
+        hq, hk, hv = (torch.empty(Bl, H, S, D, dtype=torch.bfloat16).pin_memory() for _ in range(3))
+        for h_, d_ in ((hq, q), (hk, k), (hv, v)):
+            h_.copy_(d_)
+        hout = torch.empty(Bl, H, S, D, dtype=torch.bfloat16).pin_memory()
+        hlse = torch.empty(Bl, H, S, dtype=torch.float32).pin_memory()
+        chunks = 8
+        tfa.fwd_host(hq, hk, hv, hout, hlse, causal, scale, n_chunks=chunks)          # warm (allocates workspace)
+        barrier()
+        e2e_steps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            tfa.fwd_host(hq, hk, hv, hout, hlse, causal, scale, n_chunks=chunks)
+        barrier()
+        te = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            tt = torch.tensor([te], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            te = float(tt.item())
+        same = bool(torch.equal(hout[0, 0], out[0, 0].cpu()))
+        e2e = {"value": F_job / te / 1e12, "unit": "TFLOP/s",
+               "h2d_bytes_per_step": int(3 * q.numel() * 2 * world), "d2h_bytes_per_step": int((out.numel() * 2 + lse.numel() * 4) * world),
+               "ms_per_step": te * 1e3, "api": "tfa_fwd_host (C ABI, pinned host buffers, 8 chunks on 4 streams)",
+               "matches_device_path": same, "timer": "host wall clock around synchronous calls"}
+        tfa.lib().tfa_host_release()
+        del hq, hk, hv, hout, hlse
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0 extras: parity spot check, other configs, cpu baseline ----
+    parity = None
+    try:
+        b0, h0 = 0, 0
+        qf, kf, vf = q[b0, h0].float(), k[b0, h0].float(), v[b0, h0].float()
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        s_ = (qf @ kf.t()) * scale
+        s_.masked_fill_(torch.ones(S, S, device=dev, dtype=torch.bool).triu_(1), float("-inf"))
+        want = torch.softmax(s_, dim=-1) @ vf
+        torch.backends.cuda.matmul.allow_tf32 = old
+        diff = (out[b0, h0].float() - want).abs()
+        ok = diff <= 1e-3 + 1e-3 * want.abs()
+        parity = {"vs": "fp32 torch softmax(scale QK^T)V, head (0,0)", "max_abs_err": float(diff.max()),
+                  "pass_frac_rtol1e-3_atol1e-3": float(ok.float().mean())}
+        del s_, want
+    except Exception as e:  # noqa: BLE001
+        parity = {"error": repr(e)}
+
+    configs = {}
+    if world == 1 and not args.no_extras:
+        del q, k, v, out, lse
+        torch.cuda.empty_cache()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for name, (b_, h_, s_, d_, c_) in EXTRA_CONFIGS.items():
+            qq, kk, vv = make_inputs(b_, h_, s_, d_, 20, dev, torch.bfloat16)
+            oo = torch.empty_like(qq)
+            ll = torch.empty(b_, h_, s_, dtype=torch.float32, device=dev)
+            mean, med, mn = time_kernel(tfa, qq, kk, vv, c_, 1.0 / math.sqrt(d_), oo, ll, reps=20, warm=5, flush=flush)
+            Fe, Fs = flops_effective(b_, h_, s_, d_), flops_std(b_, h_, s_, d_, c_)
+            configs[name] = {"ms": med * 1e3, "tflops": Fe / med / 1e12, "tflops_std": Fs / med / 1e12,
+                             "roofline_frac": Fe / med / 1e12 / peak, "roofline_frac_std": Fs / med / 1e12 / peak,
+                             "l2": "256 MB flush between reps"}
+            del qq, kk, vv, oo, ll
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        try:
+            fn, kind, cores = cpu_reference_runner()
+            heads, _ = pick_sample_heads(fn, S, D, causal, scale, target_s=12.0, max_heads=B * H)
+            ts = time_cpu_sample(fn, heads, S, D, causal, scale, 1, 0)
+            cpu_baseline = {"value": flops_effective(1, heads, S, D) / ts[0] / 1e12, "unit": "TFLOP/s", "cores": cores,
+                            "kind": kind, "sample": f"{heads} of {B * H} (batch*head) problems of the workload, fp32 "
+                                                    f"copies of the same-distribution inputs, 1 pass ({ts[0]:.1f} s)"}
+        except Exception as e:  # noqa: BLE001
+            cpu_baseline = {"error": repr(e)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic N(0,0.5^2), seed 20+rank, random Q/K/V",
+        "config": {"workload": W["name"], "B": B, "H": H, "S": S, "D": D, "causal": causal,
+                   "softmax_scale": "1/sqrt(D)", "parallelism": f"batch-sharded x{world}" + (" + NCCL all-gather of O" if world > 1 else ""),
+                   "flops": "2*B*H*S^2*D", "l2": "inputs (3 x %.0f MB per rank) larger than the 126 MB L2" % (q_bytes(Bl, H, S, D) / 1e6)},
+        "clocks": clk.summary(),
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "frac_of_sustained_peak": achieved / peak_sus, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}, burst)",
+                     "kernel": "fa_fwd_sm100_kernel<128,causal,bf16>", "kernel_ms_mean": k_mean * 1e3, "kernel_ms_min": k_min * 1e3,
+                     "flops_per_launch": F_launch, "traffic": PROFILED_TRAFFIC_BYTES},
+        "compute_only": {"value": compute_only_value, "unit": "TFLOP/s", "note": "kernel only, no all-gather"},
+        "cpu_baseline": cpu_baseline,
+        "parity": parity,
+        "configs": configs,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def q_bytes(B, H, S, D):
+    return B * H * S * D * 2
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the committed
+# `ncu --set full` capture (profiles/); None until a capture exists for the current kernel.
+PROFILED_TRAFFIC_BYTES = None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
