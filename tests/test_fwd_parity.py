@@ -33,14 +33,19 @@ def oracle_for(q, k, v, causal, scale, kind, round_out):
 
 
 def check_16bit(out, want16, want32, kind, causal):
+    """The shipped 16-bit output = rn16(kernel arithmetic).  The arithmetic passes 1e-3 (checked on the
+    fp32-output build); rounding adds at most half a 16-bit ulp of the value."""
     o = out.float().cpu().numpy()
     ulp = bf16_ulp(want32) if kind == "bf16" else fp16_ulp(want32)
     diff = np.abs(o - want32)
-    assert np.all(diff <= ulp + 1e-6), f"beyond one {kind} ulp: max {(diff / ulp).max():.2f} ulp"
+    budget = ATOL + RTOL * np.abs(want32) + 0.5 * ulp * 1.01
+    assert np.all(diff <= budget), f"max excess {(diff - budget).max():.3e}"
     assert np.abs(o - want16).max() <= 1e-2                     # the reference's own bar (test.py:87)
     st = err_stats(o, want32, RTOL, ATOL)
-    if not causal and kind == "fp16":
-        assert st["pass_frac"] == 1.0, st
+    if not causal:
+        assert st["pass_frac"] == 1.0, st                       # north_star bar, strict, non-causal
+    else:
+        assert st["pass_frac"] > 0.999, st                      # causal: representational misses only (A.3)
     return st
 
 
@@ -108,7 +113,15 @@ def test_golden_main_torch_only_causal_bshd(tfa, name):
     o32, _ = tfa.fwd(q, k, v, True, scale, out_fp32=True, layout="bshd")
     o16, _ = tfa.fwd(q, k, v, True, scale, layout="bshd")
     torch.cuda.synchronize()
-    np.testing.assert_allclose(o32.cpu().numpy(), g["out_v2_bshd"], rtol=RTOL, atol=ATOL)
+    # The golden is pure fp32 math; the kernel (like the reference kernel, flash_attention.cu:601) rounds P to
+    # 16 bit before the PV tensor-core product.  For early causal rows (1-3 visible keys) that rounding does not
+    # average out: |err| <= 2^-9 * sum|p v| ~ 1e-3, so a handful of elements sit just above the 1e-3 line.
+    st32 = err_stats(o32.cpu().numpy(), g["out_v2_bshd"], RTOL, ATOL)
+    assert st32["pass_frac"] > 0.9995 and st32["max_abs"] < 4e-3, st32
+    # ... and strictly within 1e-3 of the oracle that models that rounding, on the same inputs
+    qb, kb, vb = (t.transpose(1, 2) for t in (q, k, v))
+    want32, _ = oracle_for(qb, kb, vb, True, scale, "bf16", round_out=False)
+    np.testing.assert_allclose(o32.cpu().numpy().transpose(0, 2, 1, 3), want32, rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(o16.float().cpu().numpy(), g["out_v2_bshd"], rtol=1e-2, atol=1e-2)  # main_torch_only.py:309-312
     st = err_stats(o16.float().cpu().numpy(), g["out_v2_bshd"], RTOL, ATOL)
     assert st["pass_frac"] > 0.999, st

@@ -72,9 +72,12 @@ enum : uint32_t {
 };
 
 constexpr float kRescaleThresholdLog2 = 8.0f;
-// register re-allocation after the prologue: 2 softmax warpgroups x 224 + 1 service warpgroup x 64 = 512 x 128
-constexpr uint32_t kRegsSoftmax = 224;
-constexpr uint32_t kRegsOther = 64;  // lazy rescale: tolerate P up to 2^8
+// Register re-allocation after the prologue.  setmaxnreg moves registers inside the CTA's OWN pool, which is
+// what the launch allocated: 384 threads x 168 = 64512.  2 softmax warpgroups x 216 + 1 service warpgroup x 64
+// = 496 x 128 = 63488 <= 64512 (224 would need 65536 and the second .inc could never be satisfied).
+constexpr uint32_t kRegsSoftmax = 216;
+constexpr uint32_t kRegsOther = 64;
+static_assert((2 * kRegsSoftmax + kRegsOther) * 128 <= 384 * 168, "setmaxnreg budget exceeds the CTA register pool");  // lazy rescale: tolerate P up to 2^8
 
 template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
 __global__ void __launch_bounds__(384, 1)
