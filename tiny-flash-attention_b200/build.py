@@ -33,7 +33,7 @@ CXX = os.environ.get("CXX", "g++")
 LIB_NAME = "libtfa_b200.so"
 EXT_NAME = "attention_cutlass" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so")
 
-CU_SOURCES = ["tfa_api.cu", "tfa_selftest.cu"]
+CU_SOURCES = ["tfa_api.cu", "tfa_selftest.cu", "tfa_microbench.cu"]
 CU_HEADERS = ["ptx_sm100.cuh", "fa_fwd_sm100.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -63,13 +63,14 @@ def _run(cmd, log):
     return time.time() - t0, proc.stdout
 
 
-def build_lib(force=False, verbose=True):
-    """nvcc -> libtfa_b200.so (C ABI)."""
-    out = os.path.join(HERE, LIB_NAME)
+def build_lib(force=False, verbose=True, variant=None, extra_flags=()):
+    """nvcc -> libtfa_b200.so (C ABI).  `variant`/`extra_flags` build a tuning variant
+    libtfa_b200_<variant>.so (selected at run time with TFA_LIB=<path>); the shipped library has neither."""
+    out = os.path.join(HERE, LIB_NAME if not variant else f"libtfa_b200_{variant}.so")
     stamp = out + ".stamp"
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in CU_HEADERS] + [os.path.join(INCLUDE, "tfa_b200.h")]
-    dig = _digest(deps, " ".join(NVCC_FLAGS))
+    dig = _digest(deps, " ".join(NVCC_FLAGS + list(extra_flags)))
     if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == dig:
         return out
     log = os.path.join(HERE, "build.log")
@@ -77,9 +78,9 @@ def build_lib(force=False, verbose=True):
     objs = []
     procs = []
     for s in srcs:  # compile TUs in parallel
-        o = os.path.join(HERE, os.path.basename(s) + ".o")
+        o = os.path.join(HERE, os.path.basename(s) + (f".{variant}" if variant else "") + ".o")
         objs.append(o)
-        cmd = [NVCC] + NVCC_FLAGS + ["-I", INCLUDE, "-c", s, "-o", o]
+        cmd = [NVCC] + NVCC_FLAGS + list(extra_flags) + ["-I", INCLUDE, "-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         so, _ = p.communicate()
@@ -140,4 +141,8 @@ def build_all(force=False, torch_ext=True, verbose=True):
 
 
 if __name__ == "__main__":
-    build_all(force="--force" in sys.argv, torch_ext="--no-torch-ext" not in sys.argv)
+    if "--variant" in sys.argv:      # python build.py --variant emu4 -DTFA_EMU_PAIRS_PER_8=4
+        i = sys.argv.index("--variant")
+        build_lib(force=True, variant=sys.argv[i + 1], extra_flags=[a for a in sys.argv[i + 2:] if a.startswith("-D")])
+    else:
+        build_all(force="--force" in sys.argv, torch_ext="--no-torch-ext" not in sys.argv)

@@ -18,6 +18,8 @@
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
+#include <cstdio>
+#include <string>
 #include <vector>
 
 #include "../../include/tfa_b200.h"
@@ -31,10 +33,20 @@ namespace {
   TFA_CHECK_CUDA(x);       \
   TFA_CHECK_CONTIGUOUS(x)
 
+// NOTE: every message below is ONE preformatted string.  Multi-argument TORCH_CHECK formats through
+// std::ostream inside this module, and this image's g++ emits weak libstdc++ stream symbols into the .so that
+// crash once the CUDA user-mode driver is loaded (seen on the B200 box: SIGSEGV in ostream::_M_insert<long>).
+std::string fmt_msg(const char* fmt, long long a = 0, long long b = 0, long long c = 0, long long d = 0,
+                    long long e = 0) {
+  char buf[256];
+  std::snprintf(buf, sizeof(buf), fmt, a, b, c, d, e);
+  return std::string(buf);
+}
+
 void check_common(const torch::Tensor& q, const torch::Tensor& k, const torch::Tensor& v) {
-  TORCH_CHECK(q.dim() == 4, "q must have 4 dimensions, got ", q.dim());
+  TORCH_CHECK(q.dim() == 4, fmt_msg("q must have 4 dimensions, got %lld", static_cast<long long>(q.dim())));
   TORCH_CHECK(q.scalar_type() == at::kHalf || q.scalar_type() == at::kBFloat16,
-              "q must be float16 or bfloat16, got ", q.scalar_type());
+              "q must be float16 or bfloat16");
   TORCH_CHECK(k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type(),
               "q, k, v must have the same dtype");
   TORCH_CHECK(k.sizes() == q.sizes() && v.sizes() == q.sizes(),
@@ -47,45 +59,52 @@ void raise_on_error(int rc) {
   if (rc == TFA_EDEVICE_FAULT) {
     unsigned int rec[8];
     tfa_debug_record(rec);
-    TORCH_CHECK(false, tfa_error_string(rc), " [block ", rec[1], " thread ", rec[2], " site ", rec[3], " iter ", rec[4],
-                " parity ", rec[5], "]");
+    TORCH_CHECK(false, std::string(tfa_error_string(rc)) +
+                           fmt_msg(" [block %lld thread %lld site %lld iter %lld parity %lld]", rec[1], rec[2], rec[3],
+                                   rec[4], rec[5]));
   }
-  TORCH_CHECK(false, "attention_cutlass: ", tfa_error_string(rc), " (code ", rc, ")");
+  TORCH_CHECK(false, std::string("attention_cutlass: ") + tfa_error_string(rc) + fmt_msg(" (code %lld)", rc));
 }
 
 std::vector<torch::Tensor> fwd_generic(const torch::Tensor& q, const torch::Tensor& k, const torch::Tensor& v,
                                        bool is_causal, float softmax_scale, bool bshd, bool out_fp32) {
   check_common(q, k, v);
-  c10::cuda::CUDAGuard guard(q.device());
   const int64_t d0 = q.size(0), d1 = q.size(1), d2 = q.size(2), D = q.size(3);
   const int64_t B = d0, H = bshd ? d2 : d1, S = bshd ? d1 : d2;
-  TORCH_CHECK(D == 64 || D == 128, "head_dim must be 64 or 128, got ", D);
+  TORCH_CHECK(D == 64 || D == 128, fmt_msg("head_dim must be 64 or 128, got %lld", static_cast<long long>(D)));
   TORCH_CHECK(B >= 1 && H >= 1 && S >= 1, "empty tensors are not supported");
 
-  auto out = out_fp32 ? torch::empty(q.sizes(), q.options().dtype(at::kFloat)) : torch::empty_like(q);
-  auto lse = torch::empty({B, H, S}, q.options().dtype(at::kFloat));
+  torch::Tensor out, lse;
+  int rc = 0;
+  {
+    // all validation happens above: nothing below throws while the device guard is live
+    c10::cuda::CUDAGuard guard(q.device());
+    out = out_fp32 ? torch::empty(q.sizes(), q.options().dtype(at::kFloat)) : torch::empty_like(q);
+    lse = torch::empty({B, H, S}, q.options().dtype(at::kFloat));
 
-  tfa_fwd_args a;
-  a.q = q.data_ptr();
-  a.k = k.data_ptr();
-  a.v = v.data_ptr();
-  a.out = out.data_ptr();
-  a.lse = lse.data_ptr<float>();
-  a.B = static_cast<int32_t>(B);
-  a.H = static_cast<int32_t>(H);
-  a.S = static_cast<int32_t>(S);
-  a.D = static_cast<int32_t>(D);
-  if (bshd) {
-    a.stride_b = S * H * D; a.stride_s = H * D; a.stride_h = D;
-  } else {
-    a.stride_b = H * S * D; a.stride_h = S * D; a.stride_s = D;
+    tfa_fwd_args a;
+    a.q = q.data_ptr();
+    a.k = k.data_ptr();
+    a.v = v.data_ptr();
+    a.out = out.data_ptr();
+    a.lse = lse.data_ptr<float>();
+    a.B = static_cast<int32_t>(B);
+    a.H = static_cast<int32_t>(H);
+    a.S = static_cast<int32_t>(S);
+    a.D = static_cast<int32_t>(D);
+    if (bshd) {
+      a.stride_b = S * H * D; a.stride_s = H * D; a.stride_h = D;
+    } else {
+      a.stride_b = H * S * D; a.stride_h = S * D; a.stride_s = D;
+    }
+    a.dtype = q.scalar_type() == at::kBFloat16 ? TFA_BF16 : TFA_FP16;
+    a.is_causal = is_causal ? 1 : 0;
+    a.softmax_scale = softmax_scale;
+    a.out_fp32 = out_fp32 ? 1 : 0;
+    a.stream = at::cuda::getCurrentCUDAStream(q.device().index()).stream();
+    rc = tfa_fwd_ex(&a);
   }
-  a.dtype = q.scalar_type() == at::kBFloat16 ? TFA_BF16 : TFA_FP16;
-  a.is_causal = is_causal ? 1 : 0;
-  a.softmax_scale = softmax_scale;
-  a.out_fp32 = out_fp32 ? 1 : 0;
-  a.stream = at::cuda::getCurrentCUDAStream(q.device().index()).stream();
-  raise_on_error(tfa_fwd_ex(&a));
+  raise_on_error(rc);
   return {out, lse};
 }
 

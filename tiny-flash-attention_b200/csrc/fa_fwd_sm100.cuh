@@ -46,7 +46,27 @@ struct FwdParams {
   float scale;        // softmax_scale
   float scale_log2;   // softmax_scale * log2(e)
   DebugRecord* dbg;
+  unsigned long long* trace;   // TFA_TRACE builds only: [4 roles][512] (clock64 << 8 | event id)
+  int trace_block;
 };
+
+// ---- optional in-kernel timeline tracing (variant builds with -DTFA_TRACE; zero cost otherwise) ----
+#ifdef TFA_TRACE
+#define TFA_TRACE_DECL(role_expr)                                                         \
+  const bool trace_on = (p.trace != nullptr) && (static_cast<int>(blockIdx.x) == p.trace_block); \
+  unsigned long long* trace_ptr = p.trace + (role_expr) * 512;                            \
+  int trace_n = 0;
+#define TFA_TRACE_EV(id)                                                                  \
+  do {                                                                                    \
+    if (trace_on && trace_n < 511) {                                                      \
+      trace_ptr[1 + trace_n++] = (static_cast<unsigned long long>(clock64()) << 8) | static_cast<unsigned>(id); \
+      trace_ptr[0] = trace_n;                                                             \
+    }                                                                                     \
+  } while (0)
+#else
+#define TFA_TRACE_DECL(role_expr)
+#define TFA_TRACE_EV(id) do { } while (0)
+#endif
 
 template <int D>
 struct FwdCfg {
@@ -57,7 +77,7 @@ struct FwdCfg {
   static constexpr int SLAB_BYTES = 128 * 128;      // 128 rows x 128 B
   static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
   static constexpr int NSTAGE = (D == 128) ? 4 : 8; // K/V ring depth (tiles)
-  static constexpr int NUM_BARS = 2 + 2 * NSTAGE + 2 + 2 + 2;
+  static constexpr int NUM_BARS = 2 + 2 * NSTAGE + 2 + 2 + 2 + 2;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + 2 * TILE_BYTES + NSTAGE * TILE_BYTES + NUM_BARS * 8 + 16;
   // TMEM columns (fp32): S0 | S1 | O0 | O1 ; P_t aliases the first 64 columns of S_t
   static constexpr int TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 256 + D;
@@ -68,16 +88,23 @@ struct FwdCfg {
 // watchdog call sites
 enum : uint32_t {
   SITE_LOAD_EMPTY = 1, SITE_MMA_K0 = 2, SITE_MMA_Q = 3, SITE_MMA_V = 4, SITE_MMA_P = 5, SITE_MMA_K = 6,
-  SITE_SM_S = 7, SITE_EPI_O = 8
+  SITE_SM_S = 7, SITE_EPI_O = 8, SITE_MMA_PH = 9
 };
 
-constexpr float kRescaleThresholdLog2 = 8.0f;
+constexpr float kRescaleThresholdLog2 = 8.0f;  // lazy rescale: tolerate P up to 2^8
+// Of every 8 element pairs, this many use the polynomial exp2 instead of MUFU.  Measured on B200 (r01):
+// with the two-stage P hand-off, D=128 is best at 2 (+4.6%), D=64 at 3 (+20%).  -DTFA_EMU_PAIRS_PER_8=n overrides both (tuning).
+#ifdef TFA_EMU_PAIRS_PER_8
+template <int D> constexpr int kEmuPairsPer8For = TFA_EMU_PAIRS_PER_8;
+#else
+template <int D> constexpr int kEmuPairsPer8For = (D == 64) ? 3 : 2;
+#endif
 // Register re-allocation after the prologue.  setmaxnreg moves registers inside the CTA's OWN pool, which is
 // what the launch allocated: 384 threads x 168 = 64512.  2 softmax warpgroups x 216 + 1 service warpgroup x 64
 // = 496 x 128 = 63488 <= 64512 (224 would need 65536 and the second .inc could never be satisfied).
 constexpr uint32_t kRegsSoftmax = 216;
 constexpr uint32_t kRegsOther = 64;
-static_assert((2 * kRegsSoftmax + kRegsOther) * 128 <= 384 * 168, "setmaxnreg budget exceeds the CTA register pool");  // lazy rescale: tolerate P up to 2^8
+static_assert((2 * kRegsSoftmax + kRegsOther) * 128 <= 384 * 168, "setmaxnreg budget exceeds the CTA register pool");
 
 template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
 __global__ void __launch_bounds__(384, 1)
@@ -99,7 +126,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* s_full = kv_empty + NSTAGE;     // [2]
   uint64_t* p_full = s_full + 2;            // [2]
   uint64_t* o_full = p_full + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* p_half = o_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,7 +160,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&p_full[t], 4);      // one arrival per softmax warp
+      mbar_init(&p_half[t], 4);
       mbar_init(&o_full[t], 1);
     }
     fence_mbar_init();
@@ -150,6 +179,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // =========================== TMA producer ===========================
     setmaxnreg_dec<kRegsOther>();
     if (lane == 0) {
+      TFA_TRACE_DECL(3)
+      TFA_TRACE_EV(1);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (nblk[t] > 0) {
@@ -166,6 +197,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int slot = it % NSTAGE;
           const uint32_t par = (it / NSTAGE) & 1;
           mbar_wait(&kv_empty[slot], par ^ 1, p.dbg, SITE_LOAD_EMPTY, it);
+          TFA_TRACE_EV(2);
           mbar_arrive_expect_tx(&kv_full[slot], TILE);
           const CUtensorMap* tm = (kv == 0) ? &tmK : &tmV;
 #pragma unroll
@@ -177,72 +209,104 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncwarp();
   } else if (warp == 9) {
     // =========================== UMMA issuer ===========================
+    // The whole warp stays converged (descriptors live in uniform registers); one elected lane issues the
+    // tcgen05.mma / tcgen05.commit instructions.  All barrier waits that can be satisfied early (K/V tiles)
+    // are taken BEFORE the P waits, so that once P_t is ready its PV and the next S are issued back to back.
     setmaxnreg_dec<kRegsOther>();
-    if (lane == 0) {
+    {
       constexpr uint32_t FMT = IS_BF16 ? 1u : 0u;
       const uint32_t idescS = umma_idesc_f16(FMT, 128, 128, 0, 0);  // A,B K-major
       const uint32_t idescO = umma_idesc_f16(FMT, 128, D, 0, 1);    // B (=V) MN-major
       const uint32_t sQ_addr = smem_u32(sQ);
       const uint32_t sKV_addr = smem_u32(sKV);
+      TFA_TRACE_DECL(2)
+#ifdef TFA_TRACE
+      const bool trace_on_mma = trace_on && (lane == 0);
+#define TFA_TRACE_MMA(id) do { if (trace_on_mma) { TFA_TRACE_EV(id); } } while (0)
+#else
+#define TFA_TRACE_MMA(id) do { } while (0)
+#endif
+      TFA_TRACE_MMA(1);
 
-      auto issue_S = [&](int t, uint32_t k_addr) {
-        const uint32_t d_tmem = tmem_base + (t == 0 ? C::TM_S0 : C::TM_S1);
+      // S_t = Q_t K^T, then commit -> s_full[t] (and optionally release the K slot)
+      auto issue_S = [&](int t, uint32_t k_addr, uint64_t* release_bar) {
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + (t == 0 ? C::TM_S0 : C::TM_S1);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k / 4) * C::SLAB_BYTES + (k % 4) * 32;
-          const uint64_t a = umma_smem_desc(sQ_addr + t * TILE + off, 16, 1024);
-          const uint64_t b = umma_smem_desc(k_addr + off, 16, 1024);
-          umma_ss(d_tmem, a, b, idescS, k > 0 ? 1u : 0u);
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t off = (k / 4) * C::SLAB_BYTES + (k % 4) * 32;
+            const uint64_t a = umma_smem_desc(sQ_addr + t * TILE + off, 16, 1024);
+            const uint64_t b = umma_smem_desc(k_addr + off, 16, 1024);
+            umma_ss(d_tmem, a, b, idescS, k > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[t]);      // also covers every earlier MMA (incl. PV_t of the previous KV tile)
+          if (release_bar != nullptr) umma_commit(release_bar);
         }
+        __syncwarp();
       };
-      auto issue_PV = [&](int t, uint32_t v_addr, bool acc) {
-        const uint32_t d_tmem = tmem_base + (t == 0 ? C::TM_O0 : C::TM_O1);
-        const uint32_t p_tmem = tmem_base + (t == 0 ? C::TM_S0 : C::TM_S1);
+      // O_t += P_t V for k-steps [k0, k1): 16 kv rows per step = 2048 B; LBO = next 64-column slab, SBO = 8-row group
+      auto issue_PV = [&](int t, uint32_t v_addr, bool acc, int k0, int k1, uint64_t* release_bar, uint64_t* done_bar) {
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + (t == 0 ? C::TM_O0 : C::TM_O1);
+          const uint32_t p_tmem = tmem_base + (t == 0 ? C::TM_S0 : C::TM_S1);
 #pragma unroll
-        for (int k = 0; k < C::BN / 16; ++k) {
-          // 16 kv rows per step = 2048 B; LBO = next 64-column slab, SBO = next 8-row group
-          const uint64_t b = umma_smem_desc(v_addr + k * 2048, C::SLAB_BYTES, 1024);
-          umma_ts(d_tmem, p_tmem + k * 8, b, idescO, (acc || k > 0) ? 1u : 0u);
+          for (int k = 0; k < C::BN / 16; ++k) {
+            if (k >= k0 && k < k1) {
+              const uint64_t b = umma_smem_desc(v_addr + k * 2048, C::SLAB_BYTES, 1024);
+              umma_ts(d_tmem, p_tmem + k * 8, b, idescO, (acc || k > 0) ? 1u : 0u);
+            }
+          }
+          if (release_bar != nullptr) umma_commit(release_bar);
+          if (done_bar != nullptr) umma_commit(done_bar);
         }
+        __syncwarp();
       };
 
       // prologue: S_t(0) = Q_t K_0^T
       mbar_wait(&kv_full[0], 0, p.dbg, SITE_MMA_K0, 0);
+      TFA_TRACE_MMA(2);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (nblk[t] > 0) {
           mbar_wait(&q_full[t], 0, p.dbg, SITE_MMA_Q, t);
+          TFA_TRACE_MMA(3);
           tc_fence_after();
-          issue_S(t, sKV_addr);
-          umma_commit(&s_full[t]);
+          const bool last_user = (t == 1) || (nblk[1] == 0);
+          issue_S(t, sKV_addr, last_user ? &kv_empty[0] : nullptr);
+          TFA_TRACE_MMA(4);
         }
       }
-      umma_commit(&kv_empty[0]);
 
       for (int j = 0; j < nmax; ++j) {
         const int v_it = 2 * j + 1, k_it = 2 * j + 2;
         const int vslot = v_it % NSTAGE, kslot = k_it % NSTAGE;
         const uint32_t vpar = (v_it / NSTAGE) & 1, kpar = (k_it / NSTAGE) & 1;
         mbar_wait(&kv_full[vslot], vpar, p.dbg, SITE_MMA_V, j);
-        bool k_ready = false;
+        TFA_TRACE_MMA(5);
+        if (j + 1 < nmax) {
+          mbar_wait(&kv_full[kslot], kpar, p.dbg, SITE_MMA_K, j);
+          TFA_TRACE_MMA(10);
+        }
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (j >= nblk[t]) continue;
-          mbar_wait(&p_full[t], j & 1, p.dbg, SITE_MMA_P, j * 2 + t);
+          const bool last_v_user = !(t == 0 && j < nblk[1]);
+          const bool has_next = (j + 1 < nblk[t]);
+          // first half of P (keys 0..63 of the tile) is published early: start PV on it while the softmax
+          // warpgroup is still exponentiating the second half
+          mbar_wait(&p_half[t], j & 1, p.dbg, SITE_MMA_PH, j * 2 + t);
+          TFA_TRACE_MMA(6 + t);
           tc_fence_after();
-          issue_PV(t, sKV_addr + vslot * TILE, j > 0);
-          if (!(t == 0 && j < nblk[1])) umma_commit(&kv_empty[vslot]);   // last user of V_j
-          if (j + 1 < nblk[t]) {
-            if (!k_ready) {
-              mbar_wait(&kv_full[kslot], kpar, p.dbg, SITE_MMA_K, j);
-              tc_fence_after();
-              k_ready = true;
-            }
-            issue_S(t, sKV_addr + kslot * TILE);
-            umma_commit(&s_full[t]);      // also covers PV_t(j): O_t is quiescent when S_t(j+1) lands
-            if (!(t == 0 && j + 1 < nblk[1])) umma_commit(&kv_empty[kslot]);  // last user of K_{j+1}
-          } else {
-            umma_commit(&o_full[t]);
+          issue_PV(t, sKV_addr + vslot * TILE, j > 0, 0, 4, nullptr, nullptr);
+          mbar_wait(&p_full[t], j & 1, p.dbg, SITE_MMA_P, j * 2 + t);
+          TFA_TRACE_MMA(8 + t);
+          tc_fence_after();
+          issue_PV(t, sKV_addr + vslot * TILE, true, 4, 8, last_v_user ? &kv_empty[vslot] : nullptr,
+                   has_next ? nullptr : &o_full[t]);
+          if (has_next) {
+            const bool last_k_user = !(t == 0 && j + 1 < nblk[1]);
+            issue_S(t, sKV_addr + kslot * TILE, last_k_user ? &kv_empty[kslot] : nullptr);
+            TFA_TRACE_MMA(12 + t);
           }
         }
       }
@@ -262,41 +326,47 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t tO = tmem_base + lane_base + (t == 0 ? C::TM_O0 : C::TM_O1);
       const float c = p.scale_log2;
 
+      TFA_TRACE_DECL(t)
+#ifdef TFA_TRACE
+      const bool trace_on_sm = trace_on && (r == 0);
+#define TFA_TRACE_SM(id) do { if (trace_on_sm) { TFA_TRACE_EV(id); } } while (0)
+#else
+#define TFA_TRACE_SM(id) do { } while (0)
+#endif
+      TFA_TRACE_SM(1);
       float m_ref = 0.f;   // reference max the exponentials are taken against (raw score units)
       float l = 0.f;       // running sum of exp2((s - m_ref) * c)
 
       for (int j = 0; j < n; ++j) {
         mbar_wait(&s_full[t], j & 1, p.dbg, SITE_SM_S, j * 2 + t);
+        TFA_TRACE_SM(2);
         tc_fence_after();
 
+        // ---- S row -> registers in four 32-column chunks; the mask + running max of chunk i overlaps the
+        //      TMEM load of chunk i+1 ----
         uint32_t sr[128];
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) tmem_ld_x32(tS + q4 * 32, &sr[q4 * 32]);
-        tmem_wait_ld();
-
-        // ---- mask: keys beyond S, and (diagonal tile) keys after the query ----
         const int col0 = j * C::BN;
         int lim = S - col0;                                  // valid keys in this tile
-        if (CAUSAL) lim = min(lim, row_g - col0 + 1);
-        if (lim < C::BN) {
+        if (CAUSAL) lim = min(lim, row_g - col0 + 1);        // keys after the query (diagonal tile only)
+        float mxa = -INFINITY, mxb = -INFINITY;
+        tmem_ld_x32(tS, &sr[0]);
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (i >= lim) sr[i] = 0xff800000u;               // -inf
-        }
-
-        // ---- row max (thread-local) ----
-        float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]);
-        float mx2 = __uint_as_float(sr[2]), mx3 = __uint_as_float(sr[3]);
+        for (int q4 = 0; q4 < 4; ++q4) {
+          tmem_wait_ld();
+          if (q4 < 3) tmem_ld_x32(tS + (q4 + 1) * 32, &sr[(q4 + 1) * 32]);
+          if (lim < C::BN) {
 #pragma unroll
-        for (int i = 4; i < 128; i += 8) {
-          mx0 = fmax3(mx0, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
-          if (i + 4 < 128) {
-            mx2 = fmax3(mx2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
-            mx3 = fmax3(mx3, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
+            for (int i = 0; i < 32; ++i)
+              if (q4 * 32 + i >= lim) sr[q4 * 32 + i] = 0xff800000u;   // -inf
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mxa = fmax3(mxa, __uint_as_float(sr[q4 * 32 + i]), __uint_as_float(sr[q4 * 32 + i + 1]));
+            mxb = fmax3(mxb, __uint_as_float(sr[q4 * 32 + i + 2]), __uint_as_float(sr[q4 * 32 + i + 3]));
           }
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        const float mx = fmaxf(mxa, mxb);
+        TFA_TRACE_SM(3);
 
         // ---- lazy rescale of l and O (only when the max moved by more than 2^8) ----
         if (j == 0) {
@@ -321,32 +391,46 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
 
+        TFA_TRACE_SM(4);
         // ---- P = exp2(s*c - m_ref*c); l += rowsum(P) (fp32, before rounding); pack to 16 bit ----
-        const float neg_mc = -m_ref * c;
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+        // Two lanes per instruction (FFMA2/FADD2).  MUFU.EX2 (16/clk/SM) would be co-critical with the tensor
+        // pipe, so kEmuPairsPer8 of every 8 element pairs take the polynomial exp2 on the FMA/ALU pipes.
+        const float2 c2 = make_float2(c, c);
+        const float2 nm2 = make_float2(-m_ref * c, -m_ref * c);
+        constexpr int kEmuPairsPer8 = kEmuPairsPer8For<D>;
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t pk[32];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(sr[h * 64 + 2 * i + 0]), c, neg_mc));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(sr[h * 64 + 2 * i + 1]), c, neg_mc));
-            const float e2 = ex2_approx(fmaf(__uint_as_float(sr[h * 64 + 2 * i + 2]), c, neg_mc));
-            const float e3 = ex2_approx(fmaf(__uint_as_float(sr[h * 64 + 2 * i + 3]), c, neg_mc));
-            sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
-            pk[i] = pack_16x2<IS_BF16>(e0, e1);
-            pk[i + 1] = pack_16x2<IS_BF16>(e2, e3);
+          for (int i = 0; i < 32; ++i) {
+            const int pi = h * 32 + i;
+            const float2 x = ffma2(make_float2(__uint_as_float(sr[2 * pi]), __uint_as_float(sr[2 * pi + 1])), c2, nm2);
+            float2 e;
+            if (((pi * kEmuPairsPer8) & 7) < kEmuPairsPer8) {
+              e = ex2_poly2(x);
+            } else {
+              e.x = ex2_approx(x.x);
+              e.y = ex2_approx(x.y);
+            }
+            if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
+            pk[i] = pack_16x2<IS_BF16>(e.x, e.y);
           }
           tmem_st_x32(tS + h * 32, pk);     // P aliases columns [0,64) of S
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(h == 0 ? &p_half[t] : &p_full[t]);   // half 0 lets PV start on keys 0..63
+          if (h == 0) TFA_TRACE_SM(5);
         }
-        l += (sum0 + sum1) + (sum2 + sum3);
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&p_full[t]);
+        acc0 = fadd2(acc0, acc1);
+        l += acc0.x + acc0.y;
+        TFA_TRACE_SM(6);
       }
 
       // ---------------------------- epilogue ----------------------------
       mbar_wait(&o_full[t], 0, p.dbg, SITE_EPI_O, t);
+      TFA_TRACE_SM(7);
       tc_fence_after();
       const float inv_l = 1.0f / l;
       const long long tile_off = static_cast<long long>(bidx) * p.o_stride_b + static_cast<long long>(hidx) * p.o_stride_h;
@@ -404,6 +488,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (rg < S) st_global_v4(obase + static_cast<long long>(rg) * p.o_stride_s * 2 + chunk * 16, v4);
         }
       }
+      TFA_TRACE_SM(8);
       tc_fence_before();
     }
   } else {

@@ -299,6 +299,58 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2: two lanes per issue slot on the FMA pipe) ----
+__device__ __forceinline__ uint64_t f2_pack(float2 a) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(uint64_t r) {
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+// 2^x for two lanes WITHOUT the MUFU pipe: Cody-Waite split x = n + f (n = rint(x) via the 1.5*2^23 magic
+// add, f in [-0.5, 0.5]), degree-3 minimax polynomial for 2^f (max rel. error 7.5e-5, far below the 2^-9
+// rounding P gets anyway), then n is added into the exponent field with one LEA.
+// 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 LEA per pair; valid for x <= ~100, clamps x >= -126 (incl. -inf -> 2^-126).
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float M = 12582912.f;
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 t = fadd2(x, make_float2(M, M));
+  const float2 nf = fsub2(t, make_float2(M, M));
+  const float2 f = fsub2(x, nf);
+  float2 p = make_float2(0.055171601474285126f, 0.055171601474285126f);
+  p = ffma2(p, f, make_float2(0.2426111102104187f, 0.2426111102104187f));
+  p = ffma2(p, f, make_float2(0.6932610273361206f, 0.6932610273361206f));
+  p = ffma2(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
 // pack two fp32 -> one 32-bit word of 16-bit floats; `lo` lands in bits [0,16)
 template <bool IS_BF16>
 __device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {

@@ -24,6 +24,8 @@ using tfa::FwdCfg;
 using tfa::FwdParams;
 
 std::atomic<unsigned long long> g_launches{0};
+unsigned long long* g_trace_buf = nullptr;   // only read by -DTFA_TRACE variant builds
+int g_trace_block = 0;
 
 // ---- driver entry point for cuTensorMapEncodeTiled (no link-time libcuda dependency) ----
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -153,6 +155,8 @@ int fwd_impl(const tfa_fwd_args& a) {
   p.scale = a.softmax_scale;
   p.scale_log2 = a.softmax_scale * 1.4426950408889634f;
   p.dbg = g_dbg_dev;
+  p.trace = g_trace_buf;
+  p.trace_block = g_trace_block;
 
   const long long nblocks = npairs * a.B * a.H;
   if (nblocks > 0x7fffffffLL) return TFA_EINVAL_SHAPE;
@@ -283,6 +287,12 @@ unsigned long long tfa_launch_count(void) { return g_launches.load(); }
 void tfa_internal_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void* tfa_internal_dbg_dev(void) { init_dbg(); return g_dbg_dev; }
 void* tfa_internal_encode_fn(void) { return reinterpret_cast<void*>(get_encode_fn()); }
+
+// development aid (not in the public header): timeline buffer for -DTFA_TRACE variant builds
+void tfa_internal_set_trace(void* dev_buf, int block) {
+  g_trace_buf = static_cast<unsigned long long*>(dev_buf);
+  g_trace_block = block;
+}
 
 int tfa_debug_record(unsigned int out[8]) {
   if (!out) return TFA_EINVAL_PTR;
