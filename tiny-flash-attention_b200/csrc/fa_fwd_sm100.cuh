@@ -43,6 +43,8 @@ struct FwdParams {
   int H;
   int S;
   int npairs;         // ceil(S / 256)
+  int total_items;    // npairs * B * H                         (persistent variant only)
+  int* sched_counter; // zeroed before the launch; work counter  (persistent variant only)
   float scale;        // softmax_scale
   float scale_log2;   // softmax_scale * log2(e)
   DebugRecord* dbg;
@@ -228,33 +230,39 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #endif
       TFA_TRACE_MMA(1);
 
+      // Descriptor low words (start address >> 4 | LBO << 16): stepping along K or to another ring slot is ONE add.
+      // `opaque` stops the compiler from pre-computing the 16 TMEM operand addresses / descriptor words as loop
+      // invariants (it then spills them): every instruction between "barrier satisfied" and "MMA issued" is
+      // exposed tensor-pipe idle time.
+      auto opaque = [](uint32_t x) { uint32_t y; asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x)); return y; };
+      const uint32_t q_lo0 = umma_desc_lo(sQ_addr, 16), q_lo1 = umma_desc_lo(sQ_addr + TILE, 16);
+
       // S_t = Q_t K^T, then commit -> s_full[t] (and optionally release the K slot)
       auto issue_S = [&](int t, uint32_t k_addr, uint64_t* release_bar) {
+        const uint32_t q_lo = opaque((t == 0) ? q_lo0 : q_lo1);
+        const uint32_t k_lo = umma_desc_lo(k_addr, 16);
+        const uint32_t d_tmem = opaque(tmem_base) + (t == 0 ? C::TM_S0 : C::TM_S1);
         if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + (t == 0 ? C::TM_S0 : C::TM_S1);
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
-            const uint32_t off = (k / 4) * C::SLAB_BYTES + (k % 4) * 32;
-            const uint64_t a = umma_smem_desc(sQ_addr + t * TILE + off, 16, 1024);
-            const uint64_t b = umma_smem_desc(k_addr + off, 16, 1024);
-            umma_ss(d_tmem, a, b, idescS, k > 0 ? 1u : 0u);
+            const uint32_t off = (k / 4) * (C::SLAB_BYTES >> 4) + (k % 4) * 2;   // 16-byte units
+            umma_ss_lo(d_tmem, q_lo + off, k_lo + off, idescS, k > 0 ? 1u : 0u);
           }
           umma_commit(&s_full[t]);      // also covers every earlier MMA (incl. PV_t of the previous KV tile)
           if (release_bar != nullptr) umma_commit(release_bar);
         }
         __syncwarp();
       };
-      // O_t += P_t V for k-steps [k0, k1): 16 kv rows per step = 2048 B; LBO = next 64-column slab, SBO = 8-row group
+      // O_t += P_t V for k-steps [k0, k1): 16 kv rows per step = 2048 B (128 units); LBO = next 64-column slab
       auto issue_PV = [&](int t, uint32_t v_addr, bool acc, int k0, int k1, uint64_t* release_bar, uint64_t* done_bar) {
+        const uint32_t v_lo = umma_desc_lo(v_addr, C::SLAB_BYTES);
+        const uint32_t tb = opaque(tmem_base);
+        const uint32_t d_tmem = tb + (t == 0 ? C::TM_O0 : C::TM_O1);
+        const uint32_t p_tmem = tb + (t == 0 ? C::TM_S0 : C::TM_S1);
         if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + (t == 0 ? C::TM_O0 : C::TM_O1);
-          const uint32_t p_tmem = tmem_base + (t == 0 ? C::TM_S0 : C::TM_S1);
 #pragma unroll
           for (int k = 0; k < C::BN / 16; ++k) {
-            if (k >= k0 && k < k1) {
-              const uint64_t b = umma_smem_desc(v_addr + k * 2048, C::SLAB_BYTES, 1024);
-              umma_ts(d_tmem, p_tmem + k * 8, b, idescO, (acc || k > 0) ? 1u : 0u);
-            }
+            if (k >= k0 && k < k1) umma_ts_lo(d_tmem, p_tmem + k * 8, v_lo + k * 128, idescO, (acc || k > 0) ? 1u : 0u);
           }
           if (release_bar != nullptr) umma_commit(release_bar);
           if (done_bar != nullptr) umma_commit(done_bar);

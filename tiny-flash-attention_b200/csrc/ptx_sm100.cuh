@@ -59,6 +59,30 @@ __device__ __forceinline__ bool elect_one() {
 // ---------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------
+// ---- 32-bit shared-address forms (one register per barrier base instead of a 64-bit generic pointer) ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -102,11 +126,28 @@ static __device__ __noinline__ void watchdog_fire(DebugRecord* dbg, uint32_t sit
   }
   __trap();
 }
+// bounded wait, 32-bit address form.  Production builds trap inline when the bound is exceeded (no out-of-line
+// call: call sites inside the issuer's loops cost registers and forced spills); -DTFA_DEBUG_WATCHDOG builds
+// additionally record the call site in the host-mapped DebugRecord before trapping.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, DebugRecord* dbg, uint32_t site) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+#ifdef TFA_DEBUG_WATCHDOG
+    if (++spins > TFA_WATCHDOG_SPINS) watchdog_fire(dbg, site, bar, parity);
+#else
+    if (++spins > TFA_WATCHDOG_SPINS) __trap();
+#endif
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DebugRecord* dbg, uint32_t site,
                                           uint32_t iter) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef TFA_DEBUG_WATCHDOG
     if (++spins > TFA_WATCHDOG_SPINS) watchdog_fire(dbg, site, iter, parity);
+#else
+    if (++spins > TFA_WATCHDOG_SPINS) __trap();
+#endif
   }
 }
 
@@ -130,6 +171,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
       "[%6];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(x), "r"(y), "r"(z), "r"(w), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int x, int y, int z,
+                                            int w) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+      "[%6];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(x), "r"(y), "r"(z), "r"(w), "r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x,
@@ -175,6 +224,9 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // Arrive (count 1) on `bar` once every tcgen05.mma previously issued by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -209,6 +261,41 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t fmt, uint32
   d |= ((N >> 3) & 0x3Fu) << 17;
   d |= ((M >> 4) & 0x1Fu) << 24;
   return d;
+}
+
+// ---- split descriptors: the high word is a constant, the low word = start address (>>4) | LBO<<16, so stepping an
+//      operand along K (or to another ring slot) is ONE integer add on the low word.  Keeps the instruction count
+//      between "barrier satisfied" and "first MMA issued" small: that path is exposed tensor-pipe idle time. ----
+constexpr uint32_t kUmmaDescHi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // SBO=1024, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ void umma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi)
+      : "memory");
 }
 
 // D[tmem] (+)= A[smem] * B[smem]

@@ -9,12 +9,14 @@
 // caller's stream is honoured, nothing synchronises the device, nothing calls exit().
 #include "../../include/tfa_b200.h"
 #include "fa_fwd_sm100.cuh"
+#include "fa_fwd_sm100_persistent.cuh"
 
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 #include <atomic>
 #include <mutex>
 #include <vector>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -81,25 +83,74 @@ int make_tmap(CUtensorMap* m, const void* base, int dtype, int D, int S, int B, 
   return r == CUDA_SUCCESS ? 0 : TFA_EDRIVER;
 }
 
+// ---- work counters of the persistent kernel: a small pool, one int per in-flight launch ----
+constexpr int kNumSchedCounters = 256;
+int* g_sched_pool = nullptr;
+std::atomic<unsigned> g_sched_next{0};
+std::once_flag g_sched_once;
+int* next_sched_counter(cudaStream_t stream, cudaError_t* err) {
+  std::call_once(g_sched_once, [] {
+    void* d = nullptr;
+    if (cudaMalloc(&d, kNumSchedCounters * sizeof(int)) == cudaSuccess) g_sched_pool = static_cast<int*>(d);
+  });
+  if (!g_sched_pool) { *err = cudaErrorMemoryAllocation; return nullptr; }
+  int* c = g_sched_pool + (g_sched_next.fetch_add(1, std::memory_order_relaxed) % kNumSchedCounters);
+  *err = cudaMemsetAsync(c, 0, sizeof(int), stream);   // ordered before the kernel on the same stream
+  return c;
+}
+
+int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return v;
+  }();
+  return n;
+}
+
+// TFA_KERNEL=persistent selects the persistent variant (fa_fwd_sm100_persistent.cuh); default = one CTA per item.
+bool use_persistent() {
+  static int v = [] {
+    const char* e = std::getenv("TFA_KERNEL");
+    return (e != nullptr && std::strcmp(e, "persistent") == 0) ? 1 : 0;
+  }();
+  return v != 0;
+}
+
 template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
-int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FwdParams& p, int nblocks,
+int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, FwdParams p, long long nitems,
                 cudaStream_t stream) {
-  using C = FwdCfg<D>;
-  auto kern = tfa::fa_fwd_sm100_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<D>::SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_persistent_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, tfa::PFwdCfg<D>::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
-  kern<<<nblocks, C::THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  if (use_persistent()) {
+    cudaError_t cerr = cudaSuccess;
+    p.sched_counter = next_sched_counter(stream, &cerr);
+    if (cerr != cudaSuccess) return static_cast<int>(cerr);
+    const int sms = num_sms();
+    if (sms <= 0) return TFA_EARCH;
+    const int nblocks = static_cast<int>(nitems < sms ? nitems : sms);       // one CTA per SM
+    tfa::fa_fwd_sm100_persistent_kernel<D, CAUSAL, IS_BF16, OUT_F32>
+        <<<nblocks, tfa::PFwdCfg<D>::THREADS, tfa::PFwdCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  } else {
+    tfa::fa_fwd_sm100_kernel<D, CAUSAL, IS_BF16, OUT_F32>
+        <<<static_cast<int>(nitems), FwdCfg<D>::THREADS, FwdCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return static_cast<int>(cudaGetLastError());
 }
 
 template <int D>
 int dispatch(bool causal, bool bf16, bool f32, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-             const FwdParams& p, int nblocks, cudaStream_t s) {
+             const FwdParams& p, long long nblocks, cudaStream_t s) {
 #define TFA_GO(C_, B_, F_) return launch_inst<D, C_, B_, F_>(tq, tk, tv, p, nblocks, s)
   if (causal) {
     if (bf16) { if (f32) TFA_GO(true, true, true); else TFA_GO(true, true, false); }
@@ -158,11 +209,13 @@ int fwd_impl(const tfa_fwd_args& a) {
   p.trace = g_trace_buf;
   p.trace_block = g_trace_block;
 
-  const long long nblocks = npairs * a.B * a.H;
-  if (nblocks > 0x7fffffffLL) return TFA_EINVAL_SHAPE;
+  const long long nitems = npairs * a.B * a.H;
+  if (nitems > 0x3fffffffLL) return TFA_EINVAL_SHAPE;
+  p.total_items = static_cast<int>(nitems);
+  p.sched_counter = nullptr;
   const bool causal = a.is_causal != 0, bf16 = a.dtype == TFA_BF16, f32 = a.out_fp32 != 0;
-  if (a.D == 64) rc = dispatch<64>(causal, bf16, f32, tq, tk, tv, p, static_cast<int>(nblocks), stream);
-  else           rc = dispatch<128>(causal, bf16, f32, tq, tk, tv, p, static_cast<int>(nblocks), stream);
+  if (a.D == 64) rc = dispatch<64>(causal, bf16, f32, tq, tk, tv, p, nitems, stream);
+  else           rc = dispatch<128>(causal, bf16, f32, tq, tk, tv, p, nitems, stream);
   if (rc) return rc;
   return 0;
 }
