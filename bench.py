@@ -191,7 +191,7 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -252,10 +252,42 @@ def run_ours(args):
     o_full = torch.empty(B, H, S, D, dtype=torch.bfloat16, device=dev) if world > 1 else None
     peak, peak_sus, peak_src = load_peaks()
 
-    def step():
-        tfa.fwd(q, k, v, causal, scale, out=out, lse=lse)
-        if world > 1:
-            dist.all_gather_into_tensor(o_full, out)
+    # N>1: the local batch is processed in chunks; the NCCL all-gather of chunk c (async, NCCL's own stream)
+    # overlaps the kernel of chunk c+1.  Every rank ends the step holding the full O (north_star's exchange).
+    n_chunks = min(args.chunks, Bl) if world > 1 else 1
+    cb = [(Bl * c // n_chunks, Bl * (c + 1) // n_chunks) for c in range(n_chunks)]
+    stage = [torch.empty((world * (hi_ - lo_), H, S, D), dtype=torch.bfloat16, device=dev) for lo_, hi_ in cb] \
+        if world > 1 else []
+
+    kernel_events = []          # (start, end) CUDA events around every kernel launch of the timed region
+
+    def launch_kernel(lo_, hi_, record):
+        if record:
+            e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_a.record()
+        tfa.fwd(q[lo_:hi_], k[lo_:hi_], v[lo_:hi_], causal, scale, out=out[lo_:hi_], lse=lse[lo_:hi_])
+        if record:
+            e_b.record()
+            kernel_events.append((e_a, e_b))
+
+    def step(record=False):
+        if world == 1:
+            launch_kernel(0, Bl, record)
+            return
+        if n_chunks == 1:
+            launch_kernel(0, Bl, record)
+            dist.all_gather_into_tensor(o_full, out)       # straight into the batch-major result
+            return
+        works = []
+        for c, (lo_, hi_) in enumerate(cb):
+            launch_kernel(lo_, hi_, record)
+            works.append(dist.all_gather_into_tensor(stage[c], out[lo_:hi_], async_op=True))
+        for w_ in works:
+            w_.wait()
+        # staged chunks -> batch-major O (rank r owns batches [r*Bl, (r+1)*Bl))
+        of = o_full.view(world, Bl, H, S, D)
+        for c, (lo_, hi_) in enumerate(cb):
+            of[:, lo_:hi_].copy_(stage[c].view(world, hi_ - lo_, H, S, D))
 
     def barrier():
         if world > 1:
@@ -272,7 +304,7 @@ def run_ours(args):
         barrier()
         e0.record()
         for _ in range(args.steps):
-            step()
+            step(record=True)
         e1.record()
         barrier()
     launches = tfa.launch_count() - n0
@@ -285,11 +317,13 @@ def run_ours(args):
     F_job = flops_effective(B, H, S, D)
     value = F_job / t_step / 1e12
 
-    # ---- roofline: the kernel alone on this rank's shard ----
-    k_mean, k_med, k_min = time_kernel(tfa, q, k, v, causal, scale, out, lse, reps=max(args.steps, 5), warm=2)
-    F_launch = flops_effective(Bl, H, S, D)
+    # ---- roofline: the dominant (only) kernel, from the events recorded INSIDE the timed region ----
+    k_times = [a_.elapsed_time(b_) * 1e-3 for a_, b_ in kernel_events]
+    k_mean, k_min = sum(k_times) / len(k_times), min(k_times)
+    launches_per_step = len(k_times) // args.steps
+    F_launch = flops_effective(Bl, H, S, D) / launches_per_step
     achieved = F_launch / k_mean / 1e12
-    compute_only_value = achieved * world       # all ranks run the same-size shard concurrently
+    compute_only_value = flops_effective(B, H, S, D) / (k_mean * launches_per_step) / 1e12   # all ranks, kernels only
 
     # ---- e2e: host buffers through the C ABI ----
     e2e = None
@@ -378,7 +412,7 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic N(0,0.5^2), seed 20+rank, random Q/K/V",
         "config": {"workload": W["name"], "B": B, "H": H, "S": S, "D": D, "causal": causal,
-                   "softmax_scale": "1/sqrt(D)", "parallelism": f"batch-sharded x{world}" + (" + NCCL all-gather of O" if world > 1 else ""),
+                   "softmax_scale": "1/sqrt(D)", "parallelism": f"batch-sharded x{world}" + (f" + NCCL all-gather of O ({n_chunks} chunks, overlapped)" if world > 1 else ""),
                    "flops": "2*B*H*S^2*D", "l2": "inputs (3 x %.0f MB per rank) larger than the 126 MB L2" % (q_bytes(Bl, H, S, D) / 1e6)},
         "clocks": clk.summary(),
         "e2e": e2e,
@@ -386,13 +420,18 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "frac_of_sustained_peak": achieved / peak_sus, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}, burst)",
                      "kernel": "fa_fwd_sm100_kernel<128,causal,bf16>", "kernel_ms_mean": k_mean * 1e3, "kernel_ms_min": k_min * 1e3,
-                     "flops_per_launch": F_launch, "traffic": PROFILED_TRAFFIC_BYTES},
+                     "timing": "CUDA events around each launch inside the timed region",
+                     "flops_per_launch": F_launch, "launches_per_step_per_rank": launches_per_step,
+                     "traffic": PROFILED_DRAM_BYTES_PER_HEAD * (Bl * H) / launches_per_step,
+                     "traffic_source": "profiles/r01_final_cfg5shard_ncu_full_summary.txt: dram read+write of one "
+                                       "B8 H32 launch (1060.6 MB for 1077.9 MB algorithmic), scaled by heads per launch",
+                     "algorithmic_bytes_per_launch": (4 * S * D * 2 + 4 * S) * (Bl * H) / launches_per_step},
         "compute_only": {"value": compute_only_value, "unit": "TFLOP/s", "note": "kernel only, no all-gather"},
         "cpu_baseline": cpu_baseline,
         "parity": parity,
         "configs": configs,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -402,12 +441,27 @@ def q_bytes(B, H, S, D):
     return B * H * S * D * 2
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the committed
-# `ncu --set full` capture (profiles/); None until a capture exists for the current kernel.
-PROFILED_TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel from the committed
+# `ncu --set full` capture (profiles/r01_final_cfg5shard_ncu_full_summary.txt: 805.39 MB + 255.18 MB for
+# B=8 x H=32 heads of S=4096, D=128), expressed per (batch*head) problem.
+PROFILED_DRAM_BYTES_PER_HEAD = (805.391872e6 + 255.183104e6) / 256.0
+
+
+def emit(line: dict) -> None:
+    """Print THE one JSON line on the real stdout (everything else -- NCCL banners, torch.distributed chatter --
+    was diverted to stderr in main())."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    # keep stdout clean for the driver: fd 1 -> stderr for the whole run, the JSON line goes to the saved fd
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -416,6 +470,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--chunks", type=int, default=1, help="N>1: batch chunks per rank (gather/compute overlap)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
