@@ -285,16 +285,23 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
 
+      // K/V readiness is confirmed one KV tile AHEAD, in the shadow of the first-half PV of tile 1 (the tensor pipe
+      // is busy with those MMAs and the issuer is about to wait for P1 anyway).  A satisfied mbarrier wait still costs
+      // ~200 cycles of issuer time; at the top of the loop that was pure tensor-pipe idle time in front of PV0.
+      bool kv_confirmed = false;              // V_j and K_{j+1} of the upcoming iteration already waited for
       for (int j = 0; j < nmax; ++j) {
         const int v_it = 2 * j + 1, k_it = 2 * j + 2;
         const int vslot = v_it % NSTAGE, kslot = k_it % NSTAGE;
         const uint32_t vpar = (v_it / NSTAGE) & 1, kpar = (k_it / NSTAGE) & 1;
-        mbar_wait(&kv_full[vslot], vpar, p.dbg, SITE_MMA_V, j);
-        TFA_TRACE_MMA(5);
-        if (j + 1 < nmax) {
-          mbar_wait(&kv_full[kslot], kpar, p.dbg, SITE_MMA_K, j);
-          TFA_TRACE_MMA(10);
+        if (!kv_confirmed) {
+          mbar_wait(&kv_full[vslot], vpar, p.dbg, SITE_MMA_V, j);
+          TFA_TRACE_MMA(5);
+          if (j + 1 < nmax) {
+            mbar_wait(&kv_full[kslot], kpar, p.dbg, SITE_MMA_K, j);
+            TFA_TRACE_MMA(10);
+          }
         }
+        kv_confirmed = false;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (j >= nblk[t]) continue;
@@ -306,6 +313,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           TFA_TRACE_MMA(6 + t);
           tc_fence_after();
           issue_PV(t, sKV_addr + vslot * TILE, j > 0, 0, 4, nullptr, nullptr);
+          if (t == 1 && j + 1 < nmax) {
+            // look-ahead: V_{j+1} and K_{j+2} were requested a full iteration ago
+            const int v2 = 2 * j + 3, k2 = 2 * j + 4;
+            mbar_wait(&kv_full[v2 % NSTAGE], (v2 / NSTAGE) & 1, p.dbg, SITE_MMA_V, j + 1);
+            if (j + 2 < nmax) mbar_wait(&kv_full[k2 % NSTAGE], (k2 / NSTAGE) & 1, p.dbg, SITE_MMA_K, j + 1);
+            kv_confirmed = true;
+            TFA_TRACE_MMA(11);
+          }
           mbar_wait(&p_full[t], j & 1, p.dbg, SITE_MMA_P, j * 2 + t);
           TFA_TRACE_MMA(8 + t);
           tc_fence_after();

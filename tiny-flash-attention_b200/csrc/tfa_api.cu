@@ -110,13 +110,17 @@ int num_sms() {
 }
 
 // TFA_KERNEL=persistent selects the persistent variant (fa_fwd_sm100_persistent.cuh); default = one CTA per item.
-bool use_persistent() {
+// 0 = default (one CTA per work item), 1 = persistent
+int kernel_variant() {
   static int v = [] {
     const char* e = std::getenv("TFA_KERNEL");
-    return (e != nullptr && std::strcmp(e, "persistent") == 0) ? 1 : 0;
+    if (e == nullptr) return 0;
+    if (std::strcmp(e, "persistent") == 0) return 1;
+    return 0;
   }();
-  return v != 0;
+  return v;
 }
+bool use_persistent() { return kernel_variant() == 1; }
 
 template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
 int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, FwdParams p, long long nitems,
