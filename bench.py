@@ -259,6 +259,24 @@ def run_ours(args):
     stage = [torch.empty((world * (hi_ - lo_), H, S, D), dtype=torch.bfloat16, device=dev) for lo_, hi_ in cb] \
         if world > 1 else []
 
+    # exchange: "fused" = the kernel's epilogue stores O straight into every peer's gathered buffer over NVLink
+    # (sharded.FusedGather, no collective on the data path); "nccl" = kernel then ncclAllGather.
+    fused = None
+    exchange = "none"
+    if world > 1:
+        exchange = args.exchange
+        if exchange == "fused":
+            try:
+                from sharded import FusedGather
+                fused = FusedGather(B, H, S, D, torch.bfloat16, dev)
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write(f"[bench] fused exchange unavailable ({e!r}); using the NCCL all-gather\n")
+                exchange = "nccl"
+        flag = torch.tensor([1 if exchange == "fused" else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # every rank must agree
+        if int(flag.item()) == 0:
+            fused, exchange = None, "nccl"
+
     kernel_events = []          # (start, end) CUDA events around every kernel launch of the timed region
 
     def launch_kernel(lo_, hi_, record):
@@ -273,6 +291,16 @@ def run_ours(args):
     def step(record=False):
         if world == 1:
             launch_kernel(0, Bl, record)
+            return
+        if fused is not None:
+            if record:
+                e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e_a.record()
+            fused.launch(q, k, v, causal, scale, lse=lse)
+            if record:
+                e_b.record()
+                kernel_events.append((e_a, e_b))
+            fused.barrier()
             return
         if n_chunks == 1:
             launch_kernel(0, Bl, record)
@@ -293,6 +321,15 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    exchange_check = None
+    if fused is not None:
+        step()
+        dist.all_gather_into_tensor(o_full, fused.buf[lo:hi].contiguous())
+        torch.cuda.synchronize()
+        ok = torch.tensor([1 if torch.equal(fused.buf, o_full) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        exchange_check = "fused result == ncclAllGather result on every rank" if int(ok.item()) else "MISMATCH"
 
     # ---- value: K timed steps, device time, max over ranks ----
     for _ in range(max(args.warmup, 3)):
@@ -412,7 +449,10 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic N(0,0.5^2), seed 20+rank, random Q/K/V",
         "config": {"workload": W["name"], "B": B, "H": H, "S": S, "D": D, "causal": causal,
-                   "softmax_scale": "1/sqrt(D)", "parallelism": f"batch-sharded x{world}" + (f" + NCCL all-gather of O ({n_chunks} chunks, overlapped)" if world > 1 else ""),
+                   "softmax_scale": "1/sqrt(D)", "parallelism": f"batch-sharded x{world}" + ("" if world == 1 else (
+                       " + O gathered by fused NVLink peer stores in the kernel epilogue (no collective)" if fused is not None
+                       else f" + NCCL all-gather of O ({n_chunks} chunk(s))")),
+                   "exchange": exchange, "exchange_check": exchange_check,
                    "flops": "2*B*H*S^2*D", "l2": "inputs (3 x %.0f MB per rank) larger than the 126 MB L2" % (q_bytes(Bl, H, S, D) / 1e6)},
         "clocks": clk.summary(),
         "e2e": e2e,
@@ -470,6 +510,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: how O is gathered (fused peer stores in the kernel epilogue, or ncclAllGather)")
     ap.add_argument("--chunks", type=int, default=1, help="N>1: batch chunks per rank (gather/compute overlap)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -83,6 +83,13 @@ int tfa_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
 /* Device-pointer forward with explicit strides / fp32 output / stream. */
 int tfa_fwd_ex(const tfa_fwd_args* args);
 
+/* Fused compute + exchange (the reference has no multi-GPU code, BASELINE.json's north_star
+ * defines the exchange as an all-gather of O).  Same as tfa_fwd_ex(), and in the SAME kernel every 16-byte chunk
+ * of O is additionally stored to `n_extra` (<= 7) other buffers with the same strides -- the peer GPUs' copies of
+ * the gathered output, mapped into this process over NVLink (CUDA IPC / VMM / torch symmetric memory).  The stores
+ * overlap the attention math tile by tile; the caller synchronises the ranks afterwards.  16-bit output only. */
+int tfa_fwd_multi(const tfa_fwd_args* args, void* const* extra_out, int n_extra);
+
 /* Host-buffer forward: q/k/v/out/lse are HOST pointers ((B,H,S,D) contiguous; pinned
  * memory gives full PCIe speed).  Copies in, runs tfa_fwd per (batch*head) chunk on
  * `n_streams` internal streams so H2D, compute and D2H overlap, copies out, and

@@ -37,6 +37,10 @@ namespace tfa {
 
 struct FwdParams {
   void* out;          // 16-bit output, element strides below
+  // Fused exchange (multi-GPU): when n_extra_dst > 0 every 16-byte chunk of O is ALSO stored to these buffers
+  // (same strides) -- peer GPUs' copies of the gathered output, mapped over NVLink.  Replaces the all-gather.
+  void* extra_dst[7];
+  int n_extra_dst;
   float* out_f32;     // fp32 output (validation build), same strides
   float* lse;         // (BH, S) fp32 or nullptr
   long long o_stride_b, o_stride_h, o_stride_s;  // elements
@@ -508,7 +512,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int phys = (chunk & ~7) | ((chunk ^ rr) & 7);
           const uint4 v4 = *reinterpret_cast<const uint4*>(stg + rr * ROW_BYTES + phys * 16);
           const int rg = trow0 + rr;
-          if (rg < S) st_global_v4(obase + static_cast<long long>(rg) * p.o_stride_s * 2 + chunk * 16, v4);
+          if (rg < S) {
+            const long long off = tile_off * 2 + static_cast<long long>(rg) * p.o_stride_s * 2 + chunk * 16;
+            st_global_v4(obase + (off - tile_off * 2), v4);
+            for (int d = 0; d < p.n_extra_dst; ++d)          // peer copies: posted stores over NVLink
+              st_global_v4(reinterpret_cast<uint8_t*>(p.extra_dst[d]) + off, v4);
+          }
         }
       }
       TFA_TRACE_SM(8);

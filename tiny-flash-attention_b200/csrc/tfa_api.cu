@@ -176,7 +176,7 @@ bool arch_ok() {
   return ok != 0;
 }
 
-int fwd_impl(const tfa_fwd_args& a) {
+int fwd_impl(const tfa_fwd_args& a, void* const* extra_dst = nullptr, int n_extra = 0) {
   if (!a.q || !a.k || !a.v || !a.out) return TFA_EINVAL_PTR;
   if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) |
        reinterpret_cast<uintptr_t>(a.out)) & 15u)
@@ -209,6 +209,16 @@ int fwd_impl(const tfa_fwd_args& a) {
   p.npairs = static_cast<int>(npairs);
   p.scale = a.softmax_scale;
   p.scale_log2 = a.softmax_scale * 1.4426950408889634f;
+  p.n_extra_dst = 0;
+  for (int i = 0; i < 7; ++i) p.extra_dst[i] = nullptr;
+  if (n_extra > 0) {
+    if (n_extra > 7 || extra_dst == nullptr || a.out_fp32 || kernel_variant() != 0) return TFA_EINVAL_SHAPE;
+    for (int i = 0; i < n_extra; ++i) {
+      if (extra_dst[i] == nullptr || (reinterpret_cast<uintptr_t>(extra_dst[i]) & 15u)) return TFA_EINVAL_PTR;
+      p.extra_dst[i] = extra_dst[i];
+    }
+    p.n_extra_dst = n_extra;
+  }
   p.dbg = g_dbg_dev;
   p.trace = g_trace_buf;
   p.trace_block = g_trace_block;
@@ -252,6 +262,12 @@ int tfa_abi_version(void) { return TFA_ABI_VERSION; }
 int tfa_fwd_ex(const tfa_fwd_args* args) {
   if (!args) return TFA_EINVAL_PTR;
   return fwd_impl(*args);
+}
+
+int tfa_fwd_multi(const tfa_fwd_args* args, void* const* extra_out, int n_extra) {
+  if (!args) return TFA_EINVAL_PTR;
+  if (n_extra < 0) return TFA_EINVAL_SHAPE;
+  return fwd_impl(*args, extra_out, n_extra);
 }
 
 int tfa_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int S, int D, int dtype,

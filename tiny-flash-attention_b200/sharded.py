@@ -65,3 +65,55 @@ def sharded_forward(q_local, k_local, v_local, is_causal: bool, scale: float, at
     for buf, lo, hi in stage:
         out_full.view(world, Bl, *q_local.shape[1:])[:, lo:hi].copy_(buf.view(world, hi - lo, *q_local.shape[1:]))
     return out_full, (lses[0] if len(lses) == 1 else torch.cat(lses, dim=0))
+
+
+class FusedGather:
+    """Fused attention + all-gather of O over NVLink peer memory.
+
+    Every rank owns a symmetric (B_total,H,S,D) buffer (torch symmetric memory: CUDA VMM allocations mapped into every
+    rank of the node).  forward() launches ONE kernel per rank that writes its O tiles into its own slice of ALL ranks'
+    buffers -- the epilogue's coalesced 128-bit stores are simply repeated for the peer mappings, so the NVLink traffic
+    overlaps the attention math tile by tile -- then a stream-ordered symmetric-memory barrier makes every rank's
+    buffer complete.  No NCCL collective on the data path.
+    """
+
+    def __init__(self, B_total, H, S, D, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise ValueError("FusedGather supports up to 8 ranks (one NVSwitch domain)")
+        if B_total % self.world:
+            raise ValueError("batch must divide evenly across ranks")
+        self.shape = (B_total, H, S, D)
+        try:
+            symm.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:  # noqa: BLE001  (newer torch enables it implicitly)
+            pass
+        self.buf = symm.empty(self.shape, dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group.group_name)
+        self.peer_ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        self.Bl = B_total // self.world
+        self.slice_bytes = self.Bl * H * S * D * self.buf.element_size()
+
+    def launch(self, q_local, k_local, v_local, is_causal, scale, lse=None):
+        """The kernel only (asynchronous on the current stream): attention + peer stores."""
+        import tfa_ctypes as tfa
+
+        off = self.rank * self.slice_bytes
+        out_local = self.buf[self.rank * self.Bl:(self.rank + 1) * self.Bl]
+        extra = [self.peer_ptrs[r] + off for r in range(self.world) if r != self.rank]
+        _, lse = tfa.fwd_multi(q_local, k_local, v_local, is_causal, scale, out_local, extra, lse=lse)
+        return lse
+
+    def barrier(self):
+        """Stream-ordered cross-rank barrier: after it, every peer's stores into my buffer have landed."""
+        self.hdl.barrier()
+
+    def forward(self, q_local, k_local, v_local, is_causal, scale, lse=None):
+        lse = self.launch(q_local, k_local, v_local, is_causal, scale, lse=lse)
+        self.barrier()
+        return self.buf, lse

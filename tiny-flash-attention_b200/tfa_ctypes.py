@@ -47,6 +47,8 @@ def lib():
         L.tfa_fwd.restype = ci
         L.tfa_fwd_ex.argtypes = [ctypes.POINTER(FwdArgs)]
         L.tfa_fwd_ex.restype = ci
+        L.tfa_fwd_multi.argtypes = [ctypes.POINTER(FwdArgs), ctypes.POINTER(ctypes.c_void_p), ci]
+        L.tfa_fwd_multi.restype = ci
         L.tfa_fwd_host.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, ci]
         L.tfa_fwd_host.restype = ci
         L.tfa_host_release.restype = None
@@ -106,6 +108,22 @@ def fwd(q, k, v, is_causal, softmax_scale, out_fp32=False, layout="bhsd", stream
     a = FwdArgs(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), B, H, S, D, sb, sh, ss,
                 _dtype_code(q), int(bool(is_causal)), float(softmax_scale), int(bool(out_fp32)), st)
     check(lib().tfa_fwd_ex(ctypes.byref(a)))
+    return out, lse
+
+
+def fwd_multi(q, k, v, is_causal, softmax_scale, out, extra_ptrs, lse=None, stream=None):
+    """Fused compute + exchange: like fwd() on (B,H,S,D) device tensors, and the same kernel also stores every chunk
+    of O to the raw device addresses in `extra_ptrs` (peer GPUs' buffers with the same strides, <= 7 of them)."""
+    import torch
+    B, H, S, D = q.shape
+    if lse is None:
+        lse = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
+    st = stream if stream is not None else torch.cuda.current_stream(q.device).cuda_stream
+    a = FwdArgs(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), B, H, S, D, H * S * D, S * D, D,
+                _dtype_code(q), int(bool(is_causal)), float(softmax_scale), 0, st)
+    n = len(extra_ptrs)
+    arr = (ctypes.c_void_p * max(n, 1))(*[ctypes.c_void_p(int(x)) for x in extra_ptrs])
+    check(lib().tfa_fwd_multi(ctypes.byref(a), arr, n))
     return out, lse
 
 
