@@ -72,7 +72,7 @@ def load_peaks():
 class ClockSampler:
     """Samples SM clock and throttle reasons DURING the timed region (NVML), as the profiling recipe asks."""
 
-    def __init__(self, index=0, period=0.02):
+    def __init__(self, index=0, period=0.004):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.max_mhz = None
@@ -362,6 +362,19 @@ def run_ours(args):
     achieved = F_launch / k_mean / 1e12
     compute_only_value = flops_effective(B, H, S, D) / (k_mean * launches_per_step) / 1e12   # all ranks, kernels only
 
+    # fused compute+collective kernel: target = slower of (FLOPs / tensor peak) and (bytes that must leave this GPU
+    # over NVLink / measured 770 GB/s per direction), per /opt/skills/guides/B200_PROFILING.md
+    fused_roofline = None
+    if fused is not None:
+        nv_bytes = (world - 1) * Bl * H * S * D * 2
+        t_flops = F_launch / (peak * 1e12)
+        t_link = nv_bytes / 770e9
+        target = max(t_flops, t_link)
+        fused_roofline = {"kernel": "fa_fwd_sm100_kernel + peer stores (tfa_fwd_multi)", "nvlink_bytes_out_per_launch": nv_bytes,
+                          "nvlink_peak_GBps": 770.0, "t_tensor_ms": t_flops * 1e3, "t_nvlink_ms": t_link * 1e3,
+                          "target_ms": target * 1e3, "achieved_ms": k_mean * 1e3, "frac": target / k_mean,
+                          "bound": "nvlink" if t_link > t_flops else "tensor"}
+
     # ---- e2e: host buffers through the C ABI ----
     e2e = None
     if not args.no_e2e:
@@ -466,6 +479,7 @@ def run_ours(args):
                      "traffic_source": "profiles/r01_final_cfg5shard_ncu_full_summary.txt: dram read+write of one "
                                        "B8 H32 launch (1060.6 MB for 1077.9 MB algorithmic), scaled by heads per launch",
                      "algorithmic_bytes_per_launch": (4 * S * D * 2 + 4 * S) * (Bl * H) / launches_per_step},
+        "fused_roofline": fused_roofline,
         "compute_only": {"value": compute_only_value, "unit": "TFLOP/s", "note": "kernel only, no all-gather"},
         "cpu_baseline": cpu_baseline,
         "parity": parity,

@@ -6,11 +6,12 @@
 // (/root/reference/flash_attention_cutlass/csrc/flash_attention.cu:373-685).  The algorithm is
 // the same FA-2 recurrence; the machine mapping is Blackwell-first:
 //
-//   * one CTA = TWO 128-row Q tiles of one (batch, head) that share every K/V tile
-//     (reference: one 64-row tile per CTA, flash_attention.cu:695-699);
+//   * one CTA = one work item = TWO 128-row Q tiles of one (batch, head) that share every K/V tile
+//     (reference: one 64-row tile per CTA, flash_attention.cu:695-699); items are launched (b,h)-major,
+//     heaviest causal item first, so a head's K/V stay L2 resident;
 //   * Q/K/V tiles are staged HBM -> shared memory by TMA (SWIZZLE_128B boxes of 64 x 128
-//     elements) behind mbarriers, a 4..6 deep K/V ring (reference: cp.async, single buffered,
-//     flash_attention.cu:521-525,556-565,581-590);
+//     elements) behind mbarriers, a 4 (D=128) or 8 (D=64) deep K/V ring (reference: cp.async, single
+//     buffered, flash_attention.cu:521-525,556-565,581-590);
 //   * S = Q K^T and O += P V run on tcgen05 tensor cores with fp32 accumulators in TMEM:
 //     S is an SS-form UMMA (both operands K-major in smem), O is a TS-form UMMA whose A operand P
 //     is read from TMEM (it aliases S) and whose B operand is the V tile consumed in place as an
@@ -18,18 +19,21 @@
 //     ldmatrix(.trans), flash_attention.cu:84-132, kernel_traits.h:26-39);
 //   * softmax is one thread == one row (tcgen05.ld 32x32b): row max / row sum are thread-local,
 //     zero shuffles (reference: quad shfl.bfly reductions, utils.h:22-91); exp is ex2.approx with
-//     scale*log2(e) folded into one FFMA; O is rescaled lazily, only when the running max moved by
+//     scale*log2(e) folded into one FFMA2 per element pair, a measured fraction of the exponentials runs as a
+//     polynomial on the FMA pipe to unload MUFU; O is rescaled lazily, only when the running max moved by
 //     more than 2^8 (reference: unconditional rescale every tile, flash_attention.cu:264-316);
 //   * the two Q tiles ping-pong: while softmax warpgroup 0 works on S0, the tensor core runs
-//     P1 V and the next Q1 K^T, and vice versa;
+//     P1 V and the next Q1 K^T, and vice versa; P is handed over in two halves so PV starts early;
 //   * causal: KV tiles above the diagonal are skipped, only the diagonal tile is masked
 //     (reference: flash_attention.cu:536-540,576-578 with 64-wide tiles);
 //   * epilogue: O/l -> 16-bit -> swizzled smem staging -> coalesced 128-bit st.global.v4
-//     (reference: flash_attention.cu:608-663), LSE by the row-owner threads (:666-683).
+//     (reference: flash_attention.cu:608-663), optionally repeated for up to 7 peer GPUs' buffers (fused
+//     all-gather, tfa_fwd_multi); LSE by the row-owner threads (:666-683).
 //
 // Warp roles (384 threads): warps 0-3 softmax/correction/epilogue for Q tile 0, warps 4-7 the same
-// for Q tile 1, warp 8 TMA producer (one lane), warp 9 TMEM allocator + UMMA issuer (one lane),
-// warps 10-11 idle (they exist so register re-allocation is warpgroup aligned).
+// for Q tile 1, warp 8 TMA producer (one lane), warp 9 TMEM allocator + UMMA issuer (warp-uniform code, one
+// elected lane issues), warps 10-11 idle (they exist so register re-allocation is warpgroup aligned).
+// Measurements, machine constants and the variants that were tried and rejected: DESIGN.md section 4.
 #pragma once
 #include "ptx_sm100.cuh"
 
