@@ -175,6 +175,24 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&o_full[t], 1);
     }
     fence_mbar_init();
+    // First loads go out BEFORE the CTA-wide sync: they need neither TMEM nor the other warps, and the ~1.3 us of
+    // first-touch TMA latency is the largest part of the per-item prologue.  Q tiles, then the first ring fill.
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (nblk[t] > 0) {
+        mbar_arrive_expect_tx(&q_full[t], TILE);
+#pragma unroll
+        for (int sl = 0; sl < C::SLABS; ++sl)
+          tma_load_4d(sQ + t * TILE + sl * C::SLAB_BYTES, &tmQ, &q_full[t], sl * 64, row0[t], hidx, bidx);
+      }
+    }
+    for (int it = 0; it < NSTAGE && it < 2 * nmax; ++it) {      // slots are empty on the first pass
+      mbar_arrive_expect_tx(&kv_full[it], TILE);
+      const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
+#pragma unroll
+      for (int sl = 0; sl < C::SLABS; ++sl)
+        tma_load_4d(sKV + it * TILE + sl * C::SLAB_BYTES, tm, &kv_full[it], sl * 64, (it >> 1) * C::BN, hidx, bidx);
+    }
   }
   if (warp == 9) {
     tmem_alloc(tmem_slot, C::TM_COLS);
@@ -191,29 +209,17 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (lane == 0) {
       TFA_TRACE_DECL(3)
       TFA_TRACE_EV(1);
+      // ring entries [0, NSTAGE) were issued in the prologue, before the CTA-wide sync
+      for (int it = NSTAGE; it < 2 * nmax; ++it) {
+        const int slot = it % NSTAGE;
+        const uint32_t par = (it / NSTAGE) & 1;
+        mbar_wait(&kv_empty[slot], par ^ 1, p.dbg, SITE_LOAD_EMPTY, it);
+        TFA_TRACE_EV(2);
+        mbar_arrive_expect_tx(&kv_full[slot], TILE);
+        const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (nblk[t] > 0) {
-          mbar_arrive_expect_tx(&q_full[t], TILE);
-#pragma unroll
-          for (int sl = 0; sl < C::SLABS; ++sl)
-            tma_load_4d(sQ + t * TILE + sl * C::SLAB_BYTES, &tmQ, &q_full[t], sl * 64, row0[t], hidx, bidx);
-        }
-      }
-      int it = 0;
-      for (int j = 0; j < nmax; ++j) {
-#pragma unroll
-        for (int kv = 0; kv < 2; ++kv, ++it) {
-          const int slot = it % NSTAGE;
-          const uint32_t par = (it / NSTAGE) & 1;
-          mbar_wait(&kv_empty[slot], par ^ 1, p.dbg, SITE_LOAD_EMPTY, it);
-          TFA_TRACE_EV(2);
-          mbar_arrive_expect_tx(&kv_full[slot], TILE);
-          const CUtensorMap* tm = (kv == 0) ? &tmK : &tmV;
-#pragma unroll
-          for (int sl = 0; sl < C::SLABS; ++sl)
-            tma_load_4d(sKV + slot * TILE + sl * C::SLAB_BYTES, tm, &kv_full[slot], sl * 64, j * C::BN, hidx, bidx);
-        }
+        for (int sl = 0; sl < C::SLABS; ++sl)
+          tma_load_4d(sKV + slot * TILE + sl * C::SLAB_BYTES, tm, &kv_full[slot], sl * 64, (it >> 1) * C::BN, hidx, bidx);
       }
     }
     __syncwarp();
