@@ -101,6 +101,12 @@ enum : uint32_t {
   SITE_SM_S = 7, SITE_EPI_O = 8, SITE_MMA_PH = 9
 };
 
+// P hand-off point: the first kPSplitQ of 4 key-quarters go to the issuer early (PV k-steps [0, 2*kPSplitQ)).
+#ifndef TFA_P_SPLITQ
+#define TFA_P_SPLITQ 2
+#endif
+constexpr int kPSplitQ = TFA_P_SPLITQ;
+static_assert(kPSplitQ >= 1 && kPSplitQ <= 3, "P split point must leave work on both sides");
 constexpr float kRescaleThresholdLog2 = 8.0f;  // lazy rescale: tolerate P up to 2^8
 // Of every 8 element pairs, this many use the polynomial exp2 instead of MUFU.  Measured on B200 (r01):
 // with the two-stage P hand-off, D=128 is best at 2 (+4.6%), D=64 at 3 (+20%).  -DTFA_EMU_PAIRS_PER_8=n overrides both (tuning).
@@ -326,7 +332,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait(&p_half[t], j & 1, p.dbg, SITE_MMA_PH, j * 2 + t);
           TFA_TRACE_MMA(6 + t);
           tc_fence_after();
-          issue_PV(t, sKV_addr + vslot * TILE, j > 0, 0, 4, nullptr, nullptr);
+          issue_PV(t, sKV_addr + vslot * TILE, j > 0, 0, 2 * kPSplitQ, nullptr, nullptr);
           if (t == 1 && j + 1 < nmax) {
             // look-ahead: V_{j+1} and K_{j+2} were requested a full iteration ago
             const int v2 = 2 * j + 3, k2 = 2 * j + 4;
@@ -338,7 +344,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait(&p_full[t], j & 1, p.dbg, SITE_MMA_P, j * 2 + t);
           TFA_TRACE_MMA(8 + t);
           tc_fence_after();
-          issue_PV(t, sKV_addr + vslot * TILE, true, 4, 8, last_v_user ? &kv_empty[vslot] : nullptr,
+          issue_PV(t, sKV_addr + vslot * TILE, true, 2 * kPSplitQ, 8, last_v_user ? &kv_empty[vslot] : nullptr,
                    has_next ? nullptr : &o_full[t]);
           if (has_next) {
             const bool last_k_user = !(t == 0 && j + 1 < nblk[1]);
@@ -379,28 +385,32 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         TFA_TRACE_SM(2);
         tc_fence_after();
 
-        // ---- S row -> registers in four 32-column chunks; the mask + running max of chunk i overlaps the
-        //      TMEM load of chunk i+1 ----
+        // ---- S row -> registers: four back-to-back 32-column TMEM loads, ONE wait (measured 2-3 % faster than
+        //      waiting per chunk to overlap the max with the next load), then mask + 4 independent max chains ----
         uint32_t sr[128];
         const int col0 = j * C::BN;
         int lim = S - col0;                                  // valid keys in this tile
         if (CAUSAL) lim = min(lim, row_g - col0 + 1);        // keys after the query (diagonal tile only)
         float mxa = -INFINITY, mxb = -INFINITY;
-        tmem_ld_x32(tS, &sr[0]);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          tmem_wait_ld();
-          if (q4 < 3) tmem_ld_x32(tS + (q4 + 1) * 32, &sr[(q4 + 1) * 32]);
-          if (lim < C::BN) {
+        for (int q4 = 0; q4 < 4; ++q4) tmem_ld_x32(tS + q4 * 32, &sr[q4 * 32]);
+        tmem_wait_ld();
+        if (lim < C::BN) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (q4 * 32 + i >= lim) sr[q4 * 32 + i] = 0xff800000u;   // -inf
+          for (int i = 0; i < 128; ++i)
+            if (i >= lim) sr[i] = 0xff800000u;                 // -inf
+        }
+        {
+          float mxc = -INFINITY, mxd = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 128; i += 8) {
+            mxa = fmax3(mxa, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
+            mxb = fmax3(mxb, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
+            mxc = fmax3(mxc, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
+            mxd = fmax3(mxd, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
           }
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            mxa = fmax3(mxa, __uint_as_float(sr[q4 * 32 + i]), __uint_as_float(sr[q4 * 32 + i + 1]));
-            mxb = fmax3(mxb, __uint_as_float(sr[q4 * 32 + i + 2]), __uint_as_float(sr[q4 * 32 + i + 3]));
-          }
+          mxa = fmaxf(mxa, mxc);
+          mxb = fmaxf(mxb, mxd);
         }
         const float mx = fmaxf(mxa, mxb);
         TFA_TRACE_SM(3);
@@ -436,12 +446,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const float2 nm2 = make_float2(-m_ref * c, -m_ref * c);
         constexpr int kEmuPairsPer8 = kEmuPairsPer8For<D>;
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        // P is produced in four quarters of 32 keys; the first kPSplitQ quarters are published early (p_half) so the
+        // issuer can start PV on them while the rest is still being exponentiated, the remainder with p_full.
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t pk[32];
+        for (int qt = 0; qt < 4; ++qt) {
+          uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int pi = h * 32 + i;
+          for (int i = 0; i < 16; ++i) {
+            const int pi = qt * 16 + i;
             const float2 x = ffma2(make_float2(__uint_as_float(sr[2 * pi]), __uint_as_float(sr[2 * pi + 1])), c2, nm2);
             float2 e;
             if (((pi * kEmuPairsPer8) & 7) < kEmuPairsPer8) {
@@ -453,12 +465,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
             pk[i] = pack_16x2<IS_BF16>(e.x, e.y);
           }
-          tmem_st_x32(tS + h * 32, pk);     // P aliases columns [0,64) of S
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(h == 0 ? &p_half[t] : &p_full[t]);   // half 0 lets PV start on keys 0..63
-          if (h == 0) TFA_TRACE_SM(5);
+          tmem_st_x16(tS + qt * 16, pk);    // P aliases columns [0,64) of S
+          if (qt == kPSplitQ - 1 || qt == 3) {
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(qt == 3 ? &p_full[t] : &p_half[t]);
+            if (qt != 3) TFA_TRACE_SM(5);
+          }
         }
         acc0 = fadd2(acc0, acc1);
         l += acc0.x + acc0.y;
