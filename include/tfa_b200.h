@@ -48,6 +48,7 @@ extern "C" {
 #define TFA_EDRIVER       (-6)  /* cuTensorMapEncodeTiled unavailable / failed    */
 #define TFA_EARCH         (-7)  /* device is not compute capability 10.x          */
 #define TFA_EDEVICE_FAULT (-8)  /* kernel watchdog fired; see tfa_debug_record()  */
+#define TFA_EINVAL_SCALE  (-9)  /* softmax_scale negative, NaN or infinite         */
 
 /* Extended argument block (POD), the analogue of Flash_fwd_params (flash.h:29-60).
  * Strides are in ELEMENTS.  The innermost (head_dim) stride must be 1.

@@ -34,7 +34,7 @@ def test_abi_version_and_error_strings(built):
     L = tfa_ctypes.lib()
     assert L.tfa_abi_version() == 1
     assert L.tfa_error_string(0) == b"success"
-    for code in range(-8, 0):
+    for code in range(-9, 0):
         assert L.tfa_error_string(code).startswith(b"tfa:")
 
 
@@ -54,6 +54,8 @@ def test_argument_validation_without_device(built):
     assert f(B=0) == -3               # TFA_EINVAL_SHAPE
     assert f(S=0) == -3
     assert f(dtype=2) == -4           # TFA_EINVAL_DTYPE
+    g = lambda sc: L.tfa_fwd(ok, ok, ok, ok, None, 1, 1, 128, 64, 0, 0, sc, None)
+    assert g(-1.0) == -9 and g(float("nan")) == -9 and g(float("inf")) == -9    # TFA_EINVAL_SCALE
     # host path validates the same way
     assert L.tfa_fwd_host(None, ok, ok, ok, None, 1, 1, 128, 64, 0, 0, 1.0, 1) == -1
     assert L.tfa_fwd_host(ok, ok, ok, ok, None, 1, 1, 128, 80, 0, 0, 1.0, 1) == -2

@@ -179,3 +179,35 @@ def test_deterministic(tfa):
     b, lb = tfa.fwd(q, k, v, True, 0.1)
     torch.cuda.synchronize()
     assert torch.equal(a, b) and torch.equal(la, lb)
+
+
+def test_persistent_variant_stays_correct(tfa):
+    """The experimental persistent kernel (TFA_KERNEL=persistent) is selected per process: check one causal and one
+    ragged case in a subprocess against the default kernel's result (bitwise: same arithmetic, same order)."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, torch
+sys.path.insert(0, os.path.join(os.environ["TFA_ROOT"], "tiny-flash-attention_b200"))
+sys.path.insert(0, os.path.join(os.environ["TFA_ROOT"], "tests"))
+import tfa_ctypes as tfa
+from helpers import ref_inputs
+for (B, H, S, D, causal) in ((2, 5, 1280, 128, True), (1, 3, 333, 64, False)):
+    q, k, v = ref_inputs(B, H, S, D, torch.bfloat16, seed=11, device="cuda")
+    o, lse = tfa.fwd(q, k, v, causal, D ** -0.5)
+    torch.cuda.synchronize()
+    torch.save((o.cpu(), lse.cpu()), os.environ["TFA_OUT"] + f"_{S}.pt")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for variant in ("default", "persistent"):
+        env = dict(os.environ, TFA_ROOT=root, TFA_OUT=f"/tmp/tfa_variant_{variant}")
+        env.pop("TFA_KERNEL", None)
+        if variant == "persistent":
+            env["TFA_KERNEL"] = "persistent"
+        p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs[variant] = [torch.load(f"/tmp/tfa_variant_{variant}_{S}.pt") for S in (1280, 333)]
+    for (a, la), (b, lb) in zip(outs["default"], outs["persistent"]):
+        assert torch.equal(a, b) and torch.equal(la, lb)

@@ -184,6 +184,8 @@ int fwd_impl(const tfa_fwd_args& a, void* const* extra_dst = nullptr, int n_extr
   if (a.D != 64 && a.D != 128) return TFA_EINVAL_DIM;
   if (a.B < 1 || a.H < 1 || a.S < 1) return TFA_EINVAL_SHAPE;
   if (a.dtype != TFA_BF16 && a.dtype != TFA_FP16) return TFA_EINVAL_DTYPE;
+  // the running max is taken on unscaled scores (as in the reference, flash_attention.cu:228,295): scale must be >= 0
+  if (!(a.softmax_scale >= 0.0f) || !(a.softmax_scale <= 3.0e38f)) return TFA_EINVAL_SCALE;
   if (a.stride_s < a.D || (a.stride_s % 8) || (a.stride_h % 8) || (a.stride_b % 8)) return TFA_EINVAL_STRIDE;
   if (!arch_ok()) return TFA_EARCH;
   init_dbg();
@@ -293,6 +295,7 @@ int tfa_fwd_host(const void* q, const void* k, const void* v, void* out, float* 
   if (D != 64 && D != 128) return TFA_EINVAL_DIM;
   if (B < 1 || H < 1 || S < 1) return TFA_EINVAL_SHAPE;
   if (dtype != TFA_BF16 && dtype != TFA_FP16) return TFA_EINVAL_DTYPE;
+  if (!(softmax_scale >= 0.0f) || !(softmax_scale <= 3.0e38f)) return TFA_EINVAL_SCALE;
   std::lock_guard<std::mutex> lk(g_ws_mu);
   const long long BH = static_cast<long long>(B) * H;
   const size_t head_bytes = static_cast<size_t>(S) * D * 2;
@@ -388,6 +391,7 @@ const char* tfa_error_string(int code) {
     case TFA_EDRIVER: return "tfa: cuTensorMapEncodeTiled unavailable or failed";
     case TFA_EARCH: return "tfa: this library only runs on compute capability 10.x (B200, sm_100a)";
     case TFA_EDEVICE_FAULT: return "tfa: kernel watchdog fired (see tfa_debug_record)";
+    case TFA_EINVAL_SCALE: return "tfa: softmax_scale must be finite and >= 0";
     default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "tfa: unknown error";
   }
 }
