@@ -445,6 +445,58 @@ def run_ours(args):
                              "l2": "256 MB flush between reps"}
             del qq, kk, vv, oo, ll
 
+    # ---- SURVEY 8f rows 2-3 (grouped K/V heads, Sq != Sk, split-KV): timed the same way, reported beside ----
+    next_rows = {}
+    if world == 1 and not args.no_extras:
+        try:
+            try:
+                hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            except Exception:  # noqa: BLE001
+                hbm_peak = 6500.0          # profiling recipe fallback
+
+            def time_general(qq, kk, vv, causal_, ns):
+                sc = 1.0 / math.sqrt(qq.shape[-1])
+                for _ in range(3):
+                    tfa.attn_fwd(qq, kk, vv, causal_, sc, num_splits=ns)
+                torch.cuda.synchronize()
+                ts = []
+                used = 1
+                for _ in range(10):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    _, _, used = tfa.attn_fwd(qq, kk, vv, causal_, sc, num_splits=ns, return_splits=True)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1) * 1e-3)
+                ts.sort()
+                return ts[len(ts) // 2], used
+
+            g = torch.Generator(device=dev).manual_seed(20)
+            mk = lambda *shape: torch.empty(*shape, dtype=torch.bfloat16, device=dev).normal_(0.0, 0.5, generator=g)
+            # (a) cfg3 with 4 query heads per K/V head
+            qq, kk, vv = mk(4, 32, 4096, 128), mk(4, 8, 4096, 128), mk(4, 8, 4096, 128)
+            med, _ = time_general(qq, kk, vv, True, 1)
+            next_rows["gqa: cfg3 with Hkv=8 (B4 Hq32 S4096 D128 causal)"] = {
+                "ms": med * 1e3, "tflops": flops_effective(4, 32, 4096, 128) / med / 1e12,
+                "roofline_frac": flops_effective(4, 32, 4096, 128) / med / 1e12 / peak}
+            del qq, kk, vv
+            # (b) few query rows, long keys: HBM-bound (K and V are read once), only split-KV fills the GPU
+            Bq, Hh, Sq_, Sk_, Dd = 1, 8, 128, 65536, 128
+            qq, kk, vv = mk(Bq, Hh, Sq_, Dd), mk(Bq, Hh, Sk_, Dd), mk(Bq, Hh, Sk_, Dd)
+            one, _ = time_general(qq, kk, vv, False, 1)
+            spl, used = time_general(qq, kk, vv, False, 0)
+            byts = 2 * Bq * Hh * Sk_ * Dd * 2 + 2 * Bq * Hh * Sq_ * Dd * 2
+            next_rows["splitkv: B1 H8 Sq128 Sk65536 D128 non-causal"] = {
+                "single_pass_ms": one * 1e3, "split_ms": spl * 1e3, "num_splits": used,
+                "speedup": one / spl, "algorithmic_GBps": byts / spl / 1e9,
+                "roofline": {"bound": "hbm", "achieved": byts / spl / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": (byts / spl / 1e9 / hbm_peak) if hbm_peak else None,
+                             "note": "forward + combine kernels together; bytes = K,V once + Q + O"}}
+            del qq, kk, vv
+        except Exception as e:  # noqa: BLE001
+            next_rows["error"] = repr(e)
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
         try:
@@ -484,6 +536,7 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
         "parity": parity,
         "configs": configs,
+        "next_rows": next_rows,
     }
     emit(line)
     if world > 1:

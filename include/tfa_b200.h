@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TFA_ABI_VERSION 1
+#define TFA_ABI_VERSION 2   /* 2: + tfa_attn_* (grouped K/V heads, Sq != Sk, split-KV) */
 
 /* dtype codes (reference: Qkv_params::is_bf16, flash.h:27) */
 #define TFA_BF16 0
@@ -49,6 +49,8 @@ extern "C" {
 #define TFA_EARCH         (-7)  /* device is not compute capability 10.x          */
 #define TFA_EDEVICE_FAULT (-8)  /* kernel watchdog fired; see tfa_debug_record()  */
 #define TFA_EINVAL_SCALE  (-9)  /* softmax_scale negative, NaN or infinite         */
+#define TFA_EINVAL_HEADS  (-10) /* Hq not a multiple of Hkv                         */
+#define TFA_EINVAL_WORKSPACE (-11) /* split-KV asked for but workspace missing/small */
 
 /* Extended argument block (POD), the analogue of Flash_fwd_params (flash.h:29-60).
  * Strides are in ELEMENTS.  The innermost (head_dim) stride must be 1.
@@ -90,6 +92,47 @@ int tfa_fwd_ex(const tfa_fwd_args* args);
  * the gathered output, mapped into this process over NVLink (CUDA IPC / VMM / torch symmetric memory).  The stores
  * overlap the attention math tile by tile; the caller synchronises the ranks afterwards.  16-bit output only. */
 int tfa_fwd_multi(const tfa_fwd_args* args, void* const* extra_out, int n_extra);
+
+/* ---- generalised problem: grouped K/V heads (GQA/MQA), Sq != Sk, split-KV ----
+ * Reference anchors: the CPU path takes k/v with their own sequence length and aligns the causal mask
+ * bottom-right, kv_len = i + 1 + (Sk - Sq)  (flash_attention_c/csrc/attn.cpp:121-124,182-183); its archived
+ * variant maps query head h to K/V head h / (Hq/Hkv)  (flash_attention_c/csrc/archive_)/attn.cpp:61,375); the
+ * CuTe path carries the same fields dead (flash_attention_cutlass/csrc/flash.h:35-44) and emits the row LSE
+ * "for backward" without a consumer (flash_attention.cu:353,615-623) -- split-KV is that consumer.
+ *
+ *   q, out : (B, Hq, Sq, D) through q_stride_* (elements, unit head_dim stride)
+ *   k, v   : (B, Hkv, Sk, D) through kv_stride_*;  Hq % Hkv == 0
+ *   lse    : (B, Hq, Sq) contiguous fp32, may be NULL
+ *   causal : query row i sees keys j <= i + (Sk - Sq).  Rows that see no key (only when Sk < Sq) get
+ *            out = 0 and lse = +inf (the CuTe epilogue's rule for an empty row, flash_attention.cu:620-623).
+ *   num_splits: 1 = one pass.  n > 1 = the key range is cut into n chunks processed by independent CTAs (fills
+ *            the GPU when B*Hq*ceil(Sq/256) is small), partial results go to `workspace`
+ *            (tfa_attn_workspace_bytes()) and a second small kernel merges them through their LSEs.
+ *            0 = let the library decide (splits only if a workspace large enough was passed).           */
+typedef struct tfa_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  float* lse;
+  int32_t B, Hq, Hkv, Sq, Sk, D;
+  int64_t q_stride_b, q_stride_h, q_stride_s;
+  int64_t kv_stride_b, kv_stride_h, kv_stride_s;
+  int32_t dtype;
+  int32_t is_causal;
+  float softmax_scale;
+  int32_t out_fp32;
+  int32_t num_splits;
+  void* workspace;          /* device memory, 16-byte aligned; may be NULL when num_splits <= 1 */
+  size_t workspace_bytes;
+  void* stream;
+} tfa_attn_args;
+
+int tfa_attn_fwd(const tfa_attn_args* args);
+/* The split count tfa_attn_fwd() would use for args->num_splits (resolves 0 = auto, clamps n), >= 1. */
+int tfa_attn_num_splits(const tfa_attn_args* args);
+/* Workspace needed for `num_splits` (as returned above): num_splits * B*Hq*Sq * (D + 1) * 4 bytes; 0 for 1. */
+size_t tfa_attn_workspace_bytes(const tfa_attn_args* args, int num_splits);
 
 /* Host-buffer forward: q/k/v/out/lse are HOST pointers ((B,H,S,D) contiguous; pinned
  * memory gives full PCIe speed).  Copies in, runs tfa_fwd per (batch*head) chunk on

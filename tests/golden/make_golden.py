@@ -93,6 +93,16 @@ def main():
             res[f"naive_causal{int(causal)}"] = ker.naive_attn(q, k, v, causal, scale).numpy()
         np.savez_compressed(os.path.join(HERE, "ref_cpp_flash_attention_c.npz"), q=q.numpy(), k=k.numpy(),
                             v=v.numpy(), scale=np.float32(scale), **res)
+        # --- 5. same module, keys longer than queries: the bottom-right aligned causal mask (attn.cpp:121-124) ---
+        torch.manual_seed(1)
+        q, k, v = torch.rand(1, 2, 96, 64), torch.rand(1, 2, 224, 64), torch.rand(1, 2, 224, 64)
+        scale = 1.0 / math.sqrt(64)
+        res = {}
+        for causal in (False, True):
+            res[f"flash_causal{int(causal)}"] = ker.flash_attn(q, k, v, causal, scale).numpy()
+            res[f"naive_causal{int(causal)}"] = ker.naive_attn(q, k, v, causal, scale).numpy()
+        np.savez_compressed(os.path.join(HERE, "ref_cpp_sq96_sk224.npz"), q=q.numpy(), k=k.numpy(), v=v.numpy(),
+                            scale=np.float32(scale), **res)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KB")

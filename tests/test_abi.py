@@ -17,7 +17,8 @@ def declared_functions():
 
 def test_header_declares_expected_entry_points():
     names = declared_functions()
-    for n in ("tfa_fwd", "tfa_fwd_ex", "tfa_fwd_host", "tfa_error_string", "tfa_abi_version",
+    for n in ("tfa_fwd", "tfa_fwd_ex", "tfa_fwd_host", "tfa_error_string", "tfa_abi_version", "tfa_fwd_multi",
+              "tfa_attn_fwd", "tfa_attn_num_splits", "tfa_attn_workspace_bytes",
               "tfa_launch_count", "tfa_debug_record", "tfa_selftest_tma", "tfa_selftest_umma"):
         assert n in names
 
@@ -32,9 +33,9 @@ def test_library_exports_every_declared_symbol(built):
 def test_abi_version_and_error_strings(built):
     import tfa_ctypes
     L = tfa_ctypes.lib()
-    assert L.tfa_abi_version() == 1
+    assert L.tfa_abi_version() == 2
     assert L.tfa_error_string(0) == b"success"
-    for code in range(-9, 0):
+    for code in range(-11, 0):
         assert L.tfa_error_string(code).startswith(b"tfa:")
 
 
@@ -60,6 +61,27 @@ def test_argument_validation_without_device(built):
     assert L.tfa_fwd_host(None, ok, ok, ok, None, 1, 1, 128, 64, 0, 0, 1.0, 1) == -1
     assert L.tfa_fwd_host(ok, ok, ok, ok, None, 1, 1, 128, 80, 0, 0, 1.0, 1) == -2
     assert L.tfa_fwd_ex(None) == -1
+    # generalised entry: same checks plus head grouping, before any device work
+    A = tfa_ctypes.AttnArgs
+    mk = lambda **kw: A(kw.get("q", base), base, base, base, None, 1, kw.get("Hq", 4), kw.get("Hkv", 2),
+                        kw.get("Sq", 128), kw.get("Sk", 256), kw.get("D", 64), 4 * 128 * 64, 128 * 64, 64,
+                        2 * 256 * 64, 256 * 64, kw.get("kss", 64), 0, 1, kw.get("scale", 0.1), 0,
+                        kw.get("ns", 1), None, 0, None)
+    call = lambda **kw: L.tfa_attn_fwd(ctypes.byref(mk(**kw)))
+    assert L.tfa_attn_fwd(None) == -1
+    assert call(q=None) == -1
+    assert call(D=32) == -2
+    assert call(Sk=0) == -3 and call(ns=-1) == -3
+    assert call(Hkv=3) == -10         # TFA_EINVAL_HEADS
+    assert call(kss=60) == -5         # TFA_EINVAL_STRIDE
+    assert call(scale=-0.5) == -9
+    # split bookkeeping is pure host arithmetic
+    a = mk(Sq=1, Sk=128 * 64, ns=8)
+    assert L.tfa_attn_num_splits(ctypes.byref(a)) == 8
+    assert L.tfa_attn_workspace_bytes(ctypes.byref(a), 8) == 8 * 1 * 4 * 1 * 65 * 4
+    assert L.tfa_attn_workspace_bytes(ctypes.byref(a), 1) == 0
+    a = mk(Sq=1, Sk=300, ns=8)        # 3 KV tiles: at most 3 non-empty splits
+    assert L.tfa_attn_num_splits(ctypes.byref(a)) == 3
 
 
 def test_no_fallback_on_cpu_only_box(built):

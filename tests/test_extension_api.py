@@ -13,7 +13,7 @@ def mod(built):
 def test_names_and_alias(mod):
     assert hasattr(mod, "flash_attention_v2_cutlass")
     assert hasattr(mod, "flash_attn_fwd")          # the name BASELINE.json uses
-    assert mod.abi_version() == 1
+    assert mod.abi_version() == 2
 
 
 def test_signature_is_positional_five_args(mod):

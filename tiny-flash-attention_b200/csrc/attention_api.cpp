@@ -140,6 +140,62 @@ std::vector<torch::Tensor> flash_attention_v2_fp32out(torch::Tensor q, torch::Te
   return fwd_generic(q, k, v, is_causal, softmax_scale, /*bshd=*/false, /*out_fp32=*/true);
 }
 
+// Generalised problem: k, v are (B, Hkv, Sk, D) with Hq % Hkv == 0 and any Sk; causal is
+// bottom-right aligned (flash_attention_c/csrc/attn.cpp:121-124; head grouping csrc/archive_)/attn.cpp:61,375).
+// num_splits: 1 = single pass, n > 1 = split-KV with an LSE merge, 0 = let the library decide.
+std::vector<torch::Tensor> flash_attention_v2_general(torch::Tensor q, torch::Tensor k, torch::Tensor v, bool is_causal,
+                                                      float softmax_scale, int64_t num_splits) {
+  TFA_CHECK_INPUT(q);
+  TFA_CHECK_INPUT(k);
+  TFA_CHECK_INPUT(v);
+  TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4, "q, k, v must have 4 dimensions");
+  TORCH_CHECK(q.scalar_type() == at::kHalf || q.scalar_type() == at::kBFloat16, "q must be float16 or bfloat16");
+  TORCH_CHECK(k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type(),
+              "q, k, v must have the same dtype");
+  TORCH_CHECK(k.sizes() == v.sizes(), "k and v must have identical shapes");
+  TORCH_CHECK(k.size(0) == q.size(0) && k.size(3) == q.size(3), "k/v must share batch and head_dim with q");
+  TORCH_CHECK(k.device() == q.device() && v.device() == q.device(), "q, k, v must be on the same device");
+  const int64_t B = q.size(0), Hq = q.size(1), Sq = q.size(2), D = q.size(3), Hkv = k.size(1), Sk = k.size(2);
+  TORCH_CHECK(D == 64 || D == 128, fmt_msg("head_dim must be 64 or 128, got %lld", static_cast<long long>(D)));
+  TORCH_CHECK(B >= 1 && Hq >= 1 && Hkv >= 1 && Sq >= 1 && Sk >= 1, "empty tensors are not supported");
+  TORCH_CHECK(Hq % Hkv == 0, fmt_msg("query heads (%lld) must be a multiple of K/V heads (%lld)",
+                                     static_cast<long long>(Hq), static_cast<long long>(Hkv)));
+  TORCH_CHECK(num_splits >= 0 && num_splits <= 1024, "num_splits must be in [0, 1024]");
+
+  torch::Tensor out, lse, ws;
+  int rc = 0;
+  {
+    c10::cuda::CUDAGuard guard(q.device());
+    out = torch::empty_like(q);
+    lse = torch::empty({B, Hq, Sq}, q.options().dtype(at::kFloat));
+    tfa_attn_args a;
+    a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr();
+    a.out = out.data_ptr(); a.lse = lse.data_ptr<float>();
+    a.B = static_cast<int32_t>(B); a.Hq = static_cast<int32_t>(Hq); a.Hkv = static_cast<int32_t>(Hkv);
+    a.Sq = static_cast<int32_t>(Sq); a.Sk = static_cast<int32_t>(Sk); a.D = static_cast<int32_t>(D);
+    a.q_stride_b = Hq * Sq * D; a.q_stride_h = Sq * D; a.q_stride_s = D;
+    a.kv_stride_b = Hkv * Sk * D; a.kv_stride_h = Sk * D; a.kv_stride_s = D;
+    a.dtype = q.scalar_type() == at::kBFloat16 ? TFA_BF16 : TFA_FP16;
+    a.is_causal = is_causal ? 1 : 0;
+    a.softmax_scale = softmax_scale;
+    a.out_fp32 = 0;
+    a.num_splits = static_cast<int32_t>(num_splits);
+    a.workspace = nullptr; a.workspace_bytes = 0;
+    a.stream = at::cuda::getCurrentCUDAStream(q.device().index()).stream();
+    const int nsplit = tfa_attn_num_splits(&a);
+    if (nsplit > 1) {
+      const size_t need = tfa_attn_workspace_bytes(&a, nsplit);
+      ws = torch::empty({static_cast<int64_t>((need + 3) / 4)}, q.options().dtype(at::kFloat));
+      a.workspace = ws.data_ptr();
+      a.workspace_bytes = need;
+      a.num_splits = nsplit;
+    }
+    rc = tfa_attn_fwd(&a);
+  }
+  raise_on_error(rc);
+  return {out, lse};
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("flash_attention_v2_cutlass", &flash_attention_v2_cutlass,
         "Flash attention v2 forward, B200-native (sm_100a tcgen05/TMEM/TMA)");
@@ -147,6 +203,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("flash_attn_fwd", &flash_attention_v2_cutlass, "alias of flash_attention_v2_cutlass");
   m.def("flash_attention_v2_bshd", &flash_attention_v2_bshd, "same op on (B,S,H,D) tensors");
   m.def("flash_attention_v2_fp32out", &flash_attention_v2_fp32out, "same op, fp32 output (validation)");
+  m.def("flash_attention_v2_general", &flash_attention_v2_general,
+        "grouped K/V heads, Sq != Sk (bottom-right causal), optional split-KV: (q, k, v, is_causal, scale, num_splits)");
   m.def("launch_count", []() { return tfa_launch_count(); }, "kernels launched by the library so far");
   m.def("abi_version", []() { return tfa_abi_version(); });
 }

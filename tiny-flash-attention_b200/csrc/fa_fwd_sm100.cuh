@@ -48,9 +48,21 @@ struct FwdParams {
   float* out_f32;     // fp32 output (validation build), same strides
   float* lse;         // (BH, S) fp32 or nullptr
   long long o_stride_b, o_stride_h, o_stride_s;  // elements
-  int H;
-  int S;
+  int H;             // query heads
+  int S;             // query rows
   int npairs;         // ceil(S / 256)
+  // Generalised problem (reference: flash_attention_c/csrc/attn.cpp:121-124,182-183 for
+  // Sq != Sk with a bottom-right aligned causal mask, csrc/archive_)/attn.cpp:61,375 for grouped K/V heads):
+  int Sk;             // keys (== S for the reference's CuTe path)
+  int causal_off;     // Sk - S >= 0: query row i sees keys j <= i + causal_off
+  int kv_group;       // query heads per K/V head (1 = MHA)
+  // split-KV: the grid carries nsplit CTAs per work item, each covering split_tiles KV tiles and writing a
+  // normalised fp32 partial O plus its LSE; tfa_splitkv_combine merges them.  nsplit == 1: split_tiles = all.
+  int nsplit;
+  int split_tiles;
+  long long part_stride;      // out_f32 elements between consecutive splits
+  long long lse_stride_bh;    // lse elements between consecutive (b,h)
+  long long lse_part_stride;  // lse elements between consecutive splits
   int total_items;    // npairs * B * H                         (persistent variant only)
   int* sched_counter; // zeroed before the launch; work counter  (persistent variant only)
   float scale;        // softmax_scale
@@ -87,7 +99,7 @@ struct FwdCfg {
   static constexpr int SLAB_BYTES = 128 * 128;      // 128 rows x 128 B
   static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
   static constexpr int NSTAGE = (D == 128) ? 4 : 8; // K/V ring depth (tiles)
-  static constexpr int NUM_BARS = 2 + 2 * NSTAGE + 2 + 2 + 2 + 2;
+  static constexpr int NUM_BARS = 2 + 2 * NSTAGE + 2 + 2 + 2 + 2 + 2;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + 2 * TILE_BYTES + NSTAGE * TILE_BYTES + NUM_BARS * 8 + 16;
   // TMEM columns (fp32): S0 | S1 | O0 | O1 ; P_t aliases the first 64 columns of S_t
   static constexpr int TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 256 + D;
@@ -98,7 +110,7 @@ struct FwdCfg {
 // watchdog call sites
 enum : uint32_t {
   SITE_LOAD_EMPTY = 1, SITE_MMA_K0 = 2, SITE_MMA_Q = 3, SITE_MMA_V = 4, SITE_MMA_P = 5, SITE_MMA_K = 6,
-  SITE_SM_S = 7, SITE_EPI_O = 8, SITE_MMA_PH = 9
+  SITE_SM_S = 7, SITE_EPI_O = 8, SITE_MMA_PH = 9, SITE_MMA_P3 = 10
 };
 
 // P hand-off point: the first kPSplitQ of 4 key-quarters go to the issuer early (PV k-steps [0, 2*kPSplitQ)).
@@ -107,7 +119,16 @@ enum : uint32_t {
 #endif
 constexpr int kPSplitQ = TFA_P_SPLITQ;
 static_assert(kPSplitQ >= 1 && kPSplitQ <= 3, "P split point must leave work on both sides");
+// Hand-off stages: 3 (default) adds a hand-off after quarter 2, so the PV tail that sits between "P complete" and the
+// next S_t on the per-tile dependency chain is 2 k-steps instead of 4 (measured +0.5..1 % on B200); 2 = p_half + p_full.
+#ifndef TFA_P_STAGES
+#define TFA_P_STAGES 3
+#endif
+static_assert(TFA_P_STAGES == 2 || (TFA_P_STAGES == 3 && TFA_P_SPLITQ == 2), "3-stage hand-off publishes after quarters 1, 2, 3");
 constexpr float kRescaleThresholdLog2 = 8.0f;  // lazy rescale: tolerate P up to 2^8
+#ifndef TFA_SPEC_MAX
+#define TFA_SPEC_MAX 0
+#endif
 // Of every 8 element pairs, this many use the polynomial exp2 instead of MUFU.  Measured on B200 (r01):
 // with the two-stage P hand-off, D=128 is best at 2 (+4.6%), D=64 at 3 (+20%).  -DTFA_EMU_PAIRS_PER_8=n overrides both (tuning).
 #ifdef TFA_EMU_PAIRS_PER_8
@@ -118,8 +139,12 @@ template <int D> constexpr int kEmuPairsPer8For = (D == 64) ? 3 : 2;
 // Register re-allocation after the prologue.  setmaxnreg moves registers inside the CTA's OWN pool, which is
 // what the launch allocated: 384 threads x 168 = 64512.  2 softmax warpgroups x 216 + 1 service warpgroup x 64
 // = 496 x 128 = 63488 <= 64512 (224 would need 65536 and the second .inc could never be satisfied).
-constexpr uint32_t kRegsSoftmax = 216;
-constexpr uint32_t kRegsOther = 64;
+#ifndef TFA_REGS_SOFTMAX
+#define TFA_REGS_SOFTMAX 216
+#define TFA_REGS_OTHER 64
+#endif
+constexpr uint32_t kRegsSoftmax = TFA_REGS_SOFTMAX;
+constexpr uint32_t kRegsOther = TFA_REGS_OTHER;
 static_assert((2 * kRegsSoftmax + kRegsOther) * 128 <= 384 * 168, "setmaxnreg budget exceeds the CTA register pool");
 
 template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
@@ -143,25 +168,34 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_full = s_full + 2;            // [2]
   uint64_t* o_full = p_full + 2;            // [2]
   uint64_t* p_half = o_full + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 2);
+  uint64_t* p_3q = p_half + 2;              // [2]  (TFA_P_STAGES == 3 only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_3q + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- work decode: (b,h) major, heaviest (largest pair index) first inside a head ----
-  const int bh = blockIdx.x / p.npairs;
-  const int pr = p.npairs - 1 - (blockIdx.x % p.npairs);
+  // ---- work decode: (b,h) major, then KV split, heaviest (largest pair index) first inside a head ----
+  const int per_bh = p.npairs * p.nsplit;
+  const int bh = blockIdx.x / per_bh;
+  const int rem = blockIdx.x - bh * per_bh;
+  const int split = rem / p.npairs;
+  const int pr = p.npairs - 1 - (rem - split * p.npairs);
   const int bidx = bh / p.H, hidx = bh % p.H;
-  const int S = p.S;
-  const int nkv_total = (S + C::BN - 1) / C::BN;
-  int row0[2], nblk[2];
+  const int hkv = hidx / p.kv_group;                   // K/V head feeding this query head
+  const int S = p.S, Sk = p.Sk;
+  const int nkv_total = (Sk + C::BN - 1) / C::BN;
+  const int jb = split * p.split_tiles;                // first KV tile of this CTA
+  int row0[2], nblk[2];                                // nblk[t] = KV tiles [jb, jb + nblk[t]) for Q tile t
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     row0[t] = pr * 256 + t * 128;
     const bool active = row0[t] < S;
-    nblk[t] = active ? (CAUSAL ? min(nkv_total, row0[t] / C::BN + 1) : nkv_total) : 0;
+    // causal: the tile's last row sees keys <= row0 + 127 + causal_off
+    const int nfull = active ? (CAUSAL ? min(nkv_total, (row0[t] + (C::BM - 1) + p.causal_off) / C::BN + 1) : nkv_total) : 0;
+    nblk[t] = max(0, min(nfull - jb, p.split_tiles));
   }
   const int nmax = max(nblk[0], nblk[1]);
+  if (nmax == 0) return;   // split-KV only: this split lies entirely above the causal diagonal (CTA-uniform)
 
   // ---- one-time setup ----
   if (warp == 8 && lane == 0) {
@@ -178,6 +212,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 4);      // one arrival per softmax warp
       mbar_init(&p_half[t], 4);
+      mbar_init(&p_3q[t], 4);
       mbar_init(&o_full[t], 1);
     }
     fence_mbar_init();
@@ -197,7 +232,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
 #pragma unroll
       for (int sl = 0; sl < C::SLABS; ++sl)
-        tma_load_4d(sKV + it * TILE + sl * C::SLAB_BYTES, tm, &kv_full[it], sl * 64, (it >> 1) * C::BN, hidx, bidx);
+        tma_load_4d(sKV + it * TILE + sl * C::SLAB_BYTES, tm, &kv_full[it], sl * 64, (jb + (it >> 1)) * C::BN, hkv, bidx);
     }
   }
   if (warp == 9) {
@@ -207,7 +242,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // Each role re-reads the TMEM base address from shared memory (volatile) instead of carrying one value across the
+  // role dispatch: a single long live range gets spilled to local memory as soon as any role is register-tight.
+  auto read_tmem_base = [&]() {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(tmem_slot)));
+    return v;
+  };
 
   if (warp == 8) {
     // =========================== TMA producer ===========================
@@ -225,7 +266,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
 #pragma unroll
         for (int sl = 0; sl < C::SLABS; ++sl)
-          tma_load_4d(sKV + slot * TILE + sl * C::SLAB_BYTES, tm, &kv_full[slot], sl * 64, (it >> 1) * C::BN, hidx, bidx);
+          tma_load_4d(sKV + slot * TILE + sl * C::SLAB_BYTES, tm, &kv_full[slot], sl * 64, (jb + (it >> 1)) * C::BN, hkv, bidx);
       }
     }
     __syncwarp();
@@ -236,6 +277,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // are taken BEFORE the P waits, so that once P_t is ready its PV and the next S are issued back to back.
     setmaxnreg_dec<kRegsOther>();
     {
+      const uint32_t tmem_base = read_tmem_base();
       constexpr uint32_t FMT = IS_BF16 ? 1u : 0u;
       const uint32_t idescS = umma_idesc_f16(FMT, 128, 128, 0, 0);  // A,B K-major
       const uint32_t idescO = umma_idesc_f16(FMT, 128, D, 0, 1);    // B (=V) MN-major
@@ -341,10 +383,18 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             kv_confirmed = true;
             TFA_TRACE_MMA(11);
           }
+#if TFA_P_STAGES == 3
+          mbar_wait(&p_3q[t], j & 1, p.dbg, SITE_MMA_P3, j * 2 + t);
+          tc_fence_after();
+          issue_PV(t, sKV_addr + vslot * TILE, true, 4, 6, nullptr, nullptr);
+          constexpr int kTailK0 = 6;
+#else
+          constexpr int kTailK0 = 2 * kPSplitQ;
+#endif
           mbar_wait(&p_full[t], j & 1, p.dbg, SITE_MMA_P, j * 2 + t);
           TFA_TRACE_MMA(8 + t);
           tc_fence_after();
-          issue_PV(t, sKV_addr + vslot * TILE, true, 2 * kPSplitQ, 8, last_v_user ? &kv_empty[vslot] : nullptr,
+          issue_PV(t, sKV_addr + vslot * TILE, true, kTailK0, 8, last_v_user ? &kv_empty[vslot] : nullptr,
                    has_next ? nullptr : &o_full[t]);
           if (has_next) {
             const bool last_k_user = !(t == 0 && j + 1 < nblk[1]);
@@ -365,6 +415,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int r = threadIdx.x & 127;                       // row inside the Q tile == TMEM lane
       const int row_g = trow0 + r;                            // global query row
       const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+      const uint32_t tmem_base = read_tmem_base();
       const uint32_t tS = tmem_base + lane_base + (t == 0 ? C::TM_S0 : C::TM_S1);
       const uint32_t tO = tmem_base + lane_base + (t == 0 ? C::TM_O0 : C::TM_O1);
       const float c = p.scale_log2;
@@ -388,10 +439,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // ---- S row -> registers: four back-to-back 32-column TMEM loads, ONE wait (measured 2-3 % faster than
         //      waiting per chunk to overlap the max with the next load), then mask + 4 independent max chains ----
         uint32_t sr[128];
-        const int col0 = j * C::BN;
-        int lim = S - col0;                                  // valid keys in this tile
-        if (CAUSAL) lim = min(lim, row_g - col0 + 1);        // keys after the query (diagonal tile only)
-        float mxa = -INFINITY, mxb = -INFINITY;
+        const int col0 = (jb + j) * C::BN;
+        int lim = Sk - col0;                                 // valid keys in this tile
+        if (CAUSAL) lim = min(lim, row_g + p.causal_off - col0 + 1);   // keys after the query (diagonal tiles only)
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) tmem_ld_x32(tS + q4 * 32, &sr[q4 * 32]);
         tmem_wait_ld();
@@ -400,8 +450,18 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int i = 0; i < 128; ++i)
             if (i >= lim) sr[i] = 0xff800000u;                 // -inf
         }
-        {
-          float mxc = -INFINITY, mxd = -INFINITY;
+        auto row_max = [&]() {
+#if TFA_SPEC_MAX
+          // off the critical path here: two chains keep the register pressure down
+          float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 128; i += 4) {
+            mxa = fmax3(mxa, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
+            mxb = fmax3(mxb, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
+          }
+          return fmaxf(mxa, mxb);
+#else
+          float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 128; i += 8) {
             mxa = fmax3(mxa, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
@@ -409,47 +469,36 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mxc = fmax3(mxc, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
             mxd = fmax3(mxd, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
           }
-          mxa = fmaxf(mxa, mxc);
-          mxb = fmaxf(mxb, mxd);
-        }
-        const float mx = fmaxf(mxa, mxb);
-        TFA_TRACE_SM(3);
-
-        // ---- lazy rescale of l and O (only when the max moved by more than 2^8) ----
-        if (j == 0) {
-          m_ref = mx;      // always finite: key 0 is visible to every row
-        } else {
+          return fmaxf(fmaxf(mxa, mxc), fmaxf(mxb, mxd));
+#endif
+        };
+        // lazy rescale of l and O: only when the row max moved by more than 2^8 (warp-uniform branch, rare)
+        auto rescale_if_needed = [&](float mx) -> bool {
           const bool need = (mx - m_ref) * c > kRescaleThresholdLog2;
-          if (__any_sync(0xffffffffu, need)) {
-            const float m_new = need ? mx : m_ref;
-            const float alpha = ex2_approx((m_ref - m_new) * c);   // == 1 when !need
-            m_ref = m_new;
-            l *= alpha;
-            // PV_t(j-1) has completed (s_full covers it) and PV_t(j) waits for p_full: O_t is ours.
+          if (!__any_sync(0xffffffffu, need)) return false;
+          const float m_new = need ? mx : m_ref;
+          const float alpha = ex2_approx((m_ref - m_new) * c);   // == 1 when !need
+          m_ref = m_new;
+          l *= alpha;
+          // PV_t(j-1) has completed (s_full covers it) and PV_t(j) waits for p_full: O_t is ours.
 #pragma unroll
-            for (int ch = 0; ch < D / 32; ++ch) {
-              uint32_t o[32];
-              tmem_ld_x32(tO + ch * 32, o);
-              tmem_wait_ld();
+          for (int ch = 0; ch < D / 32; ++ch) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + ch * 32, o);
+            tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_x32(tO + ch * 32, o);
-            }
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(tO + ch * 32, o);
           }
-        }
-
-        TFA_TRACE_SM(4);
+          return true;
+        };
         // ---- P = exp2(s*c - m_ref*c); l += rowsum(P) (fp32, before rounding); pack to 16 bit ----
         // Two lanes per instruction (FFMA2/FADD2).  MUFU.EX2 (16/clk/SM) would be co-critical with the tensor
         // pipe, so kEmuPairsPer8 of every 8 element pairs take the polynomial exp2 on the FMA/ALU pipes.
-        const float2 c2 = make_float2(c, c);
-        const float2 nm2 = make_float2(-m_ref * c, -m_ref * c);
+        // P is produced in four quarters of 32 keys, stored to TMEM as they finish (P aliases columns [0,64) of S).
         constexpr int kEmuPairsPer8 = kEmuPairsPer8For<D>;
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-        // P is produced in four quarters of 32 keys; the first kPSplitQ quarters are published early (p_half) so the
-        // issuer can start PV on them while the rest is still being exponentiated, the remainder with p_full.
-#pragma unroll
-        for (int qt = 0; qt < 4; ++qt) {
+        const float2 c2 = make_float2(c, c);
+        auto p_quarter = [&](int qt, float2 nm2, float2& acc0, float2& acc1) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -465,15 +514,61 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
             pk[i] = pack_16x2<IS_BF16>(e.x, e.y);
           }
-          tmem_st_x16(tS + qt * 16, pk);    // P aliases columns [0,64) of S
-          if (qt == kPSplitQ - 1 || qt == 3) {
+          tmem_st_x16(tS + qt * 16, pk);
+        };
+        // hand-off: the first kPSplitQ quarters are published early (p_half) so the issuer can start PV on them
+        // while the rest is still being exponentiated, the remainder with p_full.
+        auto publish = [&](int qt) {
+          if (qt == kPSplitQ - 1 || qt == 3 || (TFA_P_STAGES == 3 && qt == 2)) {
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(qt == 3 ? &p_full[t] : &p_half[t]);
+            if (lane == 0) mbar_arrive(qt == 3 ? &p_full[t] : (qt == kPSplitQ - 1 ? &p_half[t] : &p_3q[t]));
             if (qt != 3) TFA_TRACE_SM(5);
           }
+        };
+
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#if TFA_SPEC_MAX
+        // Speculative max: quarter 0 is exponentiated against the PREVIOUS reference max while the row max of
+        // this tile is still being reduced (the two instruction streams are independent, ptxas interleaves them),
+        // which takes the max chain off the S-ready -> P-ready critical path.  The speculation fails only when
+        // the lazy-rescale threshold trips (rare): then quarter 0 is redone.  Results are bit-identical.
+        if (j == 0) m_ref = fmaxf(row_max(), -1.0e30f);     // a fully masked row (split-KV) must not give -inf
+        {
+          float2 nm2 = make_float2(-m_ref * c, -m_ref * c);
+          p_quarter(0, nm2, acc0, acc1);
+          const float mx = row_max();
+          TFA_TRACE_SM(3);
+          if (rescale_if_needed(mx)) {                         // never at j == 0 (mx == m_ref)
+            nm2 = make_float2(-m_ref * c, -m_ref * c);
+            acc0 = make_float2(0.f, 0.f);
+            acc1 = make_float2(0.f, 0.f);
+            p_quarter(0, nm2, acc0, acc1);
+          }
+          TFA_TRACE_SM(4);
+          publish(0);
+#pragma unroll
+          for (int qt = 1; qt < 4; ++qt) {
+            p_quarter(qt, nm2, acc0, acc1);
+            publish(qt);
+          }
         }
+#else
+        {
+          const float mx = row_max();
+          TFA_TRACE_SM(3);
+          if (j == 0) m_ref = fmaxf(mx, -1.0e30f);            // a fully masked row (split-KV) must not give -inf
+          else rescale_if_needed(mx);
+          TFA_TRACE_SM(4);
+          const float2 nm2 = make_float2(-m_ref * c, -m_ref * c);
+#pragma unroll
+          for (int qt = 0; qt < 4; ++qt) {
+            p_quarter(qt, nm2, acc0, acc1);
+            publish(qt);
+          }
+        }
+#endif
         acc0 = fadd2(acc0, acc1);
         l += acc0.x + acc0.y;
         TFA_TRACE_SM(6);
@@ -483,14 +578,15 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&o_full[t], 0, p.dbg, SITE_EPI_O, t);
       TFA_TRACE_SM(7);
       tc_fence_after();
-      const float inv_l = 1.0f / l;
+      // l == 0 only for a split-KV partial whose keys are all masked for this row: O = 0, LSE = -inf (weight 0)
+      const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
       const long long tile_off = static_cast<long long>(bidx) * p.o_stride_b + static_cast<long long>(hidx) * p.o_stride_h;
 
       if (p.lse != nullptr && row_g < S)
-        p.lse[static_cast<long long>(bh) * S + row_g] = m_ref * p.scale + logf(l);
+        p.lse[split * p.lse_part_stride + static_cast<long long>(bh) * p.lse_stride_bh + row_g] = m_ref * p.scale + logf(l);
 
       if constexpr (OUT_F32) {
-        float* orow = p.out_f32 + tile_off + static_cast<long long>(row_g) * p.o_stride_s;
+        float* orow = p.out_f32 + split * p.part_stride + tile_off + static_cast<long long>(row_g) * p.o_stride_s;
 #pragma unroll
         for (int ch = 0; ch < D / 32; ++ch) {
           uint32_t o[32];
@@ -555,7 +651,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TM_COLS);
+    tmem_dealloc(read_tmem_base(), C::TM_COLS);
   }
 }
 

@@ -56,7 +56,8 @@ namespace tfa {
 
 // the persistent issuer carries more state: 2 x 216 + 72 = 504 x 128 = the whole 64512-register CTA pool
 constexpr uint32_t kRegsOtherPersistent = 72;
-static_assert((2 * kRegsSoftmax + kRegsOtherPersistent) * 128 <= 384 * 168, "setmaxnreg budget");
+constexpr uint32_t kRegsSoftmaxPersistent = 216;
+static_assert((2 * kRegsSoftmaxPersistent + kRegsOtherPersistent) * 128 <= 384 * 168, "setmaxnreg budget");
 
 template <int D>
 struct PFwdCfg {
@@ -423,7 +424,7 @@ fa_fwd_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __
     __syncwarp();
   } else if (warp < 8) {
     // ================= softmax / correction / epilogue warpgroup t =================
-    setmaxnreg_inc<kRegsSoftmax>();
+    setmaxnreg_inc<kRegsSoftmaxPersistent>();
     const int t = warp >> 2;
     const int r = threadIdx.x & 127;                       // row inside the Q tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;

@@ -10,6 +10,7 @@
 #include "../../include/tfa_b200.h"
 #include "fa_fwd_sm100.cuh"
 #include "fa_fwd_sm100_persistent.cuh"
+#include "fa_splitkv_combine.cuh"
 
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
@@ -135,7 +136,8 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, tfa::PFwdCfg<D>::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
-  if (use_persistent()) {
+  const bool plain = p.nsplit == 1 && p.kv_group == 1 && p.Sk == p.S;   // the persistent variant is square/MHA only
+  if (use_persistent() && plain) {
     cudaError_t cerr = cudaSuccess;
     p.sched_counter = next_sched_counter(stream, &cerr);
     if (cerr != cudaSuccess) return static_cast<int>(cerr);
@@ -176,64 +178,238 @@ bool arch_ok() {
   return ok != 0;
 }
 
-int fwd_impl(const tfa_fwd_args& a, void* const* extra_dst = nullptr, int n_extra = 0) {
+// The problem as the launcher sees it (superset of tfa_fwd_args / tfa_attn_args).
+struct Problem {
+  const void *q, *k, *v;
+  void* out;
+  float* lse;
+  int B, Hq, Hkv, Sq, Sk, D;
+  long long qsb, qsh, qss, ksb, ksh, kss;   // element strides of q/out and of k/v
+  int dtype, causal;
+  float scale;
+  int out_fp32;
+  int num_splits;
+  void* ws;
+  size_t ws_bytes;
+  cudaStream_t stream;
+};
+
+int validate(const Problem& a) {
   if (!a.q || !a.k || !a.v || !a.out) return TFA_EINVAL_PTR;
   if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) |
        reinterpret_cast<uintptr_t>(a.out)) & 15u)
     return TFA_EINVAL_PTR;
   if (a.D != 64 && a.D != 128) return TFA_EINVAL_DIM;
-  if (a.B < 1 || a.H < 1 || a.S < 1) return TFA_EINVAL_SHAPE;
+  if (a.B < 1 || a.Hq < 1 || a.Hkv < 1 || a.Sq < 1 || a.Sk < 1) return TFA_EINVAL_SHAPE;
+  if (a.Hq % a.Hkv) return TFA_EINVAL_HEADS;
   if (a.dtype != TFA_BF16 && a.dtype != TFA_FP16) return TFA_EINVAL_DTYPE;
   // the running max is taken on unscaled scores (as in the reference, flash_attention.cu:228,295): scale must be >= 0
-  if (!(a.softmax_scale >= 0.0f) || !(a.softmax_scale <= 3.0e38f)) return TFA_EINVAL_SCALE;
-  if (a.stride_s < a.D || (a.stride_s % 8) || (a.stride_h % 8) || (a.stride_b % 8)) return TFA_EINVAL_STRIDE;
+  if (!(a.scale >= 0.0f) || !(a.scale <= 3.0e38f)) return TFA_EINVAL_SCALE;
+  if (a.qss < a.D || (a.qss % 8) || (a.qsh % 8) || (a.qsb % 8)) return TFA_EINVAL_STRIDE;
+  if (a.kss < a.D || (a.kss % 8) || (a.ksh % 8) || (a.ksb % 8)) return TFA_EINVAL_STRIDE;
+  if (a.num_splits < 0) return TFA_EINVAL_SHAPE;
+  return 0;
+}
+
+// Split-KV decision.  `want` 0 = auto: split only when the plain grid would leave more than half of the SMs idle
+// and every split still gets >= 4 KV tiles; n > 1 = as asked, clamped so that no split is empty.
+int resolve_splits(const Problem& a, int want, int sms) {
+  const int sq_eff = (a.causal && a.Sk < a.Sq) ? a.Sk : a.Sq;          // rows that see at least one key
+  const long long items = ((static_cast<long long>(sq_eff) + 255) / 256) * a.B * a.Hq;
+  const int nkv = (a.Sk + 127) / 128;
+  int n = want;
+  if (n == 0) {
+    if (sms <= 0 || items * 2 > sms) return 1;
+    n = static_cast<int>((sms + items - 1) / items);
+    if (n > nkv / 4) n = nkv / 4;
+    if (n > 32) n = 32;
+  }
+  if (n > nkv) n = nkv;
+  if (n < 2) return 1;
+  const int tiles = (nkv + n - 1) / n;
+  return (nkv + tiles - 1) / tiles;                                     // drop empty tail splits
+}
+
+size_t splitkv_ws_bytes(const Problem& a, int nsplit) {
+  if (nsplit <= 1) return 0;
+  return static_cast<size_t>(nsplit) * a.B * a.Hq * a.Sq * (static_cast<size_t>(a.D) + 1) * sizeof(float);
+}
+
+template <int D>
+int launch_fill(const tfa::FillParams& fp, bool f32, cudaStream_t stream) {
+  constexpr int RPB = 256 / (D / 4);
+  const long long blocks = (fp.rows + RPB - 1) / RPB;
+  if (blocks > 0x7fffffffLL) return TFA_EINVAL_SHAPE;
+  if (f32) tfa::empty_rows_fill_kernel<D, true><<<static_cast<int>(blocks), 256, 0, stream>>>(fp);
+  else     tfa::empty_rows_fill_kernel<D, false><<<static_cast<int>(blocks), 256, 0, stream>>>(fp);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <int D>
+int launch_combine(const tfa::CombineParams& cp, bool bf16, bool f32, cudaStream_t stream) {
+  constexpr int RPB = 256 / (D / 4);
+  const long long blocks = (cp.rows + RPB - 1) / RPB;
+  if (blocks > 0x7fffffffLL) return TFA_EINVAL_SHAPE;
+  const int nb = static_cast<int>(blocks);
+  if (f32)       tfa::splitkv_combine_kernel<D, true, true><<<nb, 256, 0, stream>>>(cp);
+  else if (bf16) tfa::splitkv_combine_kernel<D, true, false><<<nb, 256, 0, stream>>>(cp);
+  else           tfa::splitkv_combine_kernel<D, false, false><<<nb, 256, 0, stream>>>(cp);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
+  int rc = validate(a);
+  if (rc) return rc;
   if (!arch_ok()) return TFA_EARCH;
   init_dbg();
+  cudaStream_t stream = a.stream;
+  const bool causal = a.causal != 0, bf16 = a.dtype == TFA_BF16, f32 = a.out_fp32 != 0;
+  const bool plain = (a.Sq == a.Sk) && (a.Hq == a.Hkv);
+  if (n_extra > 0) {
+    // fused exchange: 16-bit output of the reference-shaped problem only
+    if (n_extra > 7 || extra_dst == nullptr || f32 || kernel_variant() != 0 || !plain || a.num_splits > 1)
+      return TFA_EINVAL_SHAPE;
+    for (int i = 0; i < n_extra; ++i)
+      if (extra_dst[i] == nullptr || (reinterpret_cast<uintptr_t>(extra_dst[i]) & 15u)) return TFA_EINVAL_PTR;
+  }
 
-  const long long npairs = (static_cast<long long>(a.S) + 255) / 256;
-  cudaStream_t stream = static_cast<cudaStream_t>(a.stream);
+  int nsplit = (n_extra > 0) ? 1 : resolve_splits(a, a.num_splits, num_sms());
+  if (nsplit > 1) {
+    const size_t need = splitkv_ws_bytes(a, nsplit);
+    const bool ws_ok = a.ws != nullptr && !(reinterpret_cast<uintptr_t>(a.ws) & 15u) && a.ws_bytes >= need;
+    if (!ws_ok) {
+      if (a.num_splits == 0) nsplit = 1;               // auto: no workspace, no split
+      else return TFA_EINVAL_WORKSPACE;
+    }
+  }
+
+  const long long lse_stride_bh = a.Sq;                // of the caller's (B, Hq, Sq) tensor
+  const size_t osz = f32 ? 4 : 2;
+
+  // causal with more queries than keys: rows [0, Sq-Sk) see nothing; the rest is a square causal problem
+  if (causal && a.Sk < a.Sq) {
+    const int n_empty = a.Sq - a.Sk;
+    tfa::FillParams fp;
+    fp.out = a.out; fp.lse = a.lse;
+    fp.o_stride_b = a.qsb; fp.o_stride_h = a.qsh; fp.o_stride_s = a.qss;
+    fp.lse_stride_bh = lse_stride_bh;
+    fp.rows = static_cast<long long>(a.B) * a.Hq * n_empty;
+    fp.H = a.Hq; fp.n_empty = n_empty;
+    rc = (a.D == 64) ? launch_fill<64>(fp, f32, stream) : launch_fill<128>(fp, f32, stream);
+    if (rc) return rc;
+    a.q = static_cast<const char*>(a.q) + static_cast<size_t>(n_empty) * a.qss * 2;
+    a.out = static_cast<char*>(a.out) + static_cast<size_t>(n_empty) * a.qss * osz;
+    if (a.lse) a.lse += n_empty;
+    a.Sq = a.Sk;
+  }
+  const int causal_off = causal ? a.Sk - a.Sq : 0;     // >= 0 from here on
+
+  const long long npairs = (static_cast<long long>(a.Sq) + 255) / 256;
+  const int nkv_total = (a.Sk + 127) / 128;
+  const int split_tiles = (nkv_total + nsplit - 1) / nsplit;
 
   CUtensorMap tq, tk, tv;
-  int rc;
-  if ((rc = make_tmap(&tq, a.q, a.dtype, a.D, a.S, a.B, a.H, a.stride_b, a.stride_h, a.stride_s))) return rc;
-  if ((rc = make_tmap(&tk, a.k, a.dtype, a.D, a.S, a.B, a.H, a.stride_b, a.stride_h, a.stride_s))) return rc;
-  if ((rc = make_tmap(&tv, a.v, a.dtype, a.D, a.S, a.B, a.H, a.stride_b, a.stride_h, a.stride_s))) return rc;
+  if ((rc = make_tmap(&tq, a.q, a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss))) return rc;
+  if ((rc = make_tmap(&tk, a.k, a.dtype, a.D, a.Sk, a.B, a.Hkv, a.ksb, a.ksh, a.kss))) return rc;
+  if ((rc = make_tmap(&tv, a.v, a.dtype, a.D, a.Sk, a.B, a.Hkv, a.ksb, a.ksh, a.kss))) return rc;
+
+  const long long rows = static_cast<long long>(a.B) * a.Hq * a.Sq;
+  float* ws_o = static_cast<float*>(a.ws);
+  float* ws_lse = ws_o ? ws_o + static_cast<size_t>(nsplit) * rows * a.D : nullptr;
 
   FwdParams p;
-  p.out = a.out_fp32 ? nullptr : a.out;
-  p.out_f32 = a.out_fp32 ? static_cast<float*>(a.out) : nullptr;
-  p.lse = a.lse;
-  p.o_stride_b = a.stride_b;
-  p.o_stride_h = a.stride_h;
-  p.o_stride_s = a.stride_s;
-  p.H = a.H;
-  p.S = a.S;
+  std::memset(&p, 0, sizeof(p));
+  p.H = a.Hq;
+  p.S = a.Sq;
+  p.Sk = a.Sk;
+  p.causal_off = causal_off;
+  p.kv_group = a.Hq / a.Hkv;
   p.npairs = static_cast<int>(npairs);
-  p.scale = a.softmax_scale;
-  p.scale_log2 = a.softmax_scale * 1.4426950408889634f;
-  p.n_extra_dst = 0;
-  for (int i = 0; i < 7; ++i) p.extra_dst[i] = nullptr;
-  if (n_extra > 0) {
-    if (n_extra > 7 || extra_dst == nullptr || a.out_fp32 || kernel_variant() != 0) return TFA_EINVAL_SHAPE;
-    for (int i = 0; i < n_extra; ++i) {
-      if (extra_dst[i] == nullptr || (reinterpret_cast<uintptr_t>(extra_dst[i]) & 15u)) return TFA_EINVAL_PTR;
-      p.extra_dst[i] = extra_dst[i];
-    }
-    p.n_extra_dst = n_extra;
+  p.nsplit = nsplit;
+  p.split_tiles = split_tiles;
+  p.scale = a.scale;
+  // scale == 0 is legal (uniform attention over the visible keys): a tiny positive exponent scale keeps
+  // masked scores at -inf (0 * -inf would be NaN) while every visible score still maps to exp2(0) = 1
+  p.scale_log2 = fmaxf(a.scale * 1.4426950408889634f, 1.0e-30f);
+  if (nsplit > 1) {
+    // partials: contiguous (B, Hq, Sq, D) fp32 per split, normalised, with their LSEs
+    p.out = nullptr;
+    p.out_f32 = ws_o;
+    p.lse = ws_lse;
+    p.o_stride_s = a.D;
+    p.o_stride_h = static_cast<long long>(a.Sq) * a.D;
+    p.o_stride_b = p.o_stride_h * a.Hq;
+    p.part_stride = rows * a.D;
+    p.lse_stride_bh = a.Sq;
+    p.lse_part_stride = rows;
+  } else {
+    p.out = f32 ? nullptr : a.out;
+    p.out_f32 = f32 ? static_cast<float*>(a.out) : nullptr;
+    p.lse = a.lse;
+    p.o_stride_b = a.qsb;
+    p.o_stride_h = a.qsh;
+    p.o_stride_s = a.qss;
+    p.part_stride = 0;
+    p.lse_stride_bh = lse_stride_bh;
+    p.lse_part_stride = 0;
   }
+  for (int i = 0; i < n_extra; ++i) p.extra_dst[i] = extra_dst[i];
+  p.n_extra_dst = n_extra;
   p.dbg = g_dbg_dev;
   p.trace = g_trace_buf;
   p.trace_block = g_trace_block;
 
-  const long long nitems = npairs * a.B * a.H;
+  const long long nitems = npairs * a.B * a.Hq * nsplit;
   if (nitems > 0x3fffffffLL) return TFA_EINVAL_SHAPE;
   p.total_items = static_cast<int>(nitems);
   p.sched_counter = nullptr;
-  const bool causal = a.is_causal != 0, bf16 = a.dtype == TFA_BF16, f32 = a.out_fp32 != 0;
-  if (a.D == 64) rc = dispatch<64>(causal, bf16, f32, tq, tk, tv, p, nitems, stream);
-  else           rc = dispatch<128>(causal, bf16, f32, tq, tk, tv, p, nitems, stream);
+  const bool kernel_f32 = f32 || nsplit > 1;
+  if (a.D == 64) rc = dispatch<64>(causal, bf16, kernel_f32, tq, tk, tv, p, nitems, stream);
+  else           rc = dispatch<128>(causal, bf16, kernel_f32, tq, tk, tv, p, nitems, stream);
   if (rc) return rc;
+
+  if (nsplit > 1) {
+    tfa::CombineParams cp;
+    cp.o_part = ws_o;
+    cp.lse_part = ws_lse;
+    cp.out = a.out;
+    cp.lse = a.lse;
+    cp.o_stride_b = a.qsb; cp.o_stride_h = a.qsh; cp.o_stride_s = a.qss;
+    cp.lse_stride_bh = lse_stride_bh;
+    cp.rows = rows;
+    cp.H = a.Hq; cp.S = a.Sq;
+    cp.nsplit = nsplit; cp.split_tiles = split_tiles;
+    cp.nkv_total = nkv_total;
+    cp.causal = causal ? 1 : 0; cp.causal_off = causal_off;
+    rc = (a.D == 64) ? launch_combine<64>(cp, bf16, f32, stream) : launch_combine<128>(cp, bf16, f32, stream);
+    if (rc) return rc;
+  }
   return 0;
+}
+
+Problem from_fwd_args(const tfa_fwd_args& a) {
+  Problem q;
+  q.q = a.q; q.k = a.k; q.v = a.v; q.out = a.out; q.lse = a.lse;
+  q.B = a.B; q.Hq = a.H; q.Hkv = a.H; q.Sq = a.S; q.Sk = a.S; q.D = a.D;
+  q.qsb = q.ksb = a.stride_b; q.qsh = q.ksh = a.stride_h; q.qss = q.kss = a.stride_s;
+  q.dtype = a.dtype; q.causal = a.is_causal; q.scale = a.softmax_scale; q.out_fp32 = a.out_fp32;
+  q.num_splits = 1; q.ws = nullptr; q.ws_bytes = 0;
+  q.stream = static_cast<cudaStream_t>(a.stream);
+  return q;
+}
+
+Problem from_attn_args(const tfa_attn_args& a) {
+  Problem q;
+  q.q = a.q; q.k = a.k; q.v = a.v; q.out = a.out; q.lse = a.lse;
+  q.B = a.B; q.Hq = a.Hq; q.Hkv = a.Hkv; q.Sq = a.Sq; q.Sk = a.Sk; q.D = a.D;
+  q.qsb = a.q_stride_b; q.qsh = a.q_stride_h; q.qss = a.q_stride_s;
+  q.ksb = a.kv_stride_b; q.ksh = a.kv_stride_h; q.kss = a.kv_stride_s;
+  q.dtype = a.dtype; q.causal = a.is_causal; q.scale = a.softmax_scale; q.out_fp32 = a.out_fp32;
+  q.num_splits = a.num_splits; q.ws = a.workspace; q.ws_bytes = a.workspace_bytes;
+  q.stream = static_cast<cudaStream_t>(a.stream);
+  return q;
 }
 
 // ---- host-buffer path workspace ----
@@ -263,13 +439,30 @@ int tfa_abi_version(void) { return TFA_ABI_VERSION; }
 
 int tfa_fwd_ex(const tfa_fwd_args* args) {
   if (!args) return TFA_EINVAL_PTR;
-  return fwd_impl(*args);
+  return fwd_impl(from_fwd_args(*args));
+}
+
+int tfa_attn_fwd(const tfa_attn_args* args) {
+  if (!args) return TFA_EINVAL_PTR;
+  return fwd_impl(from_attn_args(*args));
+}
+
+int tfa_attn_num_splits(const tfa_attn_args* args) {
+  if (!args) return 1;
+  const Problem a = from_attn_args(*args);
+  if (a.B < 1 || a.Hq < 1 || a.Sq < 1 || a.Sk < 1 || a.num_splits < 0) return 1;
+  return resolve_splits(a, a.num_splits, num_sms());
+}
+
+size_t tfa_attn_workspace_bytes(const tfa_attn_args* args, int num_splits) {
+  if (!args || args->B < 1 || args->Hq < 1 || args->Sq < 1) return 0;
+  return splitkv_ws_bytes(from_attn_args(*args), num_splits);
 }
 
 int tfa_fwd_multi(const tfa_fwd_args* args, void* const* extra_out, int n_extra) {
   if (!args) return TFA_EINVAL_PTR;
   if (n_extra < 0) return TFA_EINVAL_SHAPE;
-  return fwd_impl(*args, extra_out, n_extra);
+  return fwd_impl(from_fwd_args(*args), extra_out, n_extra);
 }
 
 int tfa_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int S, int D, int dtype,
@@ -286,7 +479,7 @@ int tfa_fwd(const void* q, const void* k, const void* v, void* out, float* lse, 
   a.softmax_scale = softmax_scale;
   a.out_fp32 = 0;
   a.stream = cuda_stream;
-  return fwd_impl(a);
+  return fwd_impl(from_fwd_args(a));
 }
 
 int tfa_fwd_host(const void* q, const void* k, const void* v, void* out, float* lse, int B, int H, int S, int D,
@@ -385,13 +578,15 @@ const char* tfa_error_string(int code) {
     case 0: return "success";
     case TFA_EINVAL_PTR: return "tfa: null or misaligned (16 B) pointer";
     case TFA_EINVAL_DIM: return "tfa: head_dim must be 64 or 128";
-    case TFA_EINVAL_SHAPE: return "tfa: B, H, S must be >= 1 (and B*H*ceil(S/256) < 2^31)";
+    case TFA_EINVAL_SHAPE: return "tfa: B, H, S must be >= 1 (and B*H*ceil(S/256) < 2^30); fused exchange needs the square MHA problem";
     case TFA_EINVAL_DTYPE: return "tfa: dtype must be TFA_BF16 (0) or TFA_FP16 (1)";
     case TFA_EINVAL_STRIDE: return "tfa: strides must be multiples of 8 elements with unit head_dim stride";
     case TFA_EDRIVER: return "tfa: cuTensorMapEncodeTiled unavailable or failed";
     case TFA_EARCH: return "tfa: this library only runs on compute capability 10.x (B200, sm_100a)";
     case TFA_EDEVICE_FAULT: return "tfa: kernel watchdog fired (see tfa_debug_record)";
     case TFA_EINVAL_SCALE: return "tfa: softmax_scale must be finite and >= 0";
+    case TFA_EINVAL_HEADS: return "tfa: query heads must be a multiple of K/V heads";
+    case TFA_EINVAL_WORKSPACE: return "tfa: split-KV needs a 16-byte aligned workspace of tfa_attn_workspace_bytes()";
     default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "tfa: unknown error";
   }
 }

@@ -34,6 +34,21 @@ class FwdArgs(ctypes.Structure):
     ]
 
 
+class AttnArgs(ctypes.Structure):
+    """struct tfa_attn_args (include/tfa_b200.h)."""
+    _fields_ = [
+        ("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("v", ctypes.c_void_p), ("out", ctypes.c_void_p),
+        ("lse", ctypes.c_void_p),
+        ("B", ctypes.c_int32), ("Hq", ctypes.c_int32), ("Hkv", ctypes.c_int32), ("Sq", ctypes.c_int32),
+        ("Sk", ctypes.c_int32), ("D", ctypes.c_int32),
+        ("q_stride_b", ctypes.c_int64), ("q_stride_h", ctypes.c_int64), ("q_stride_s", ctypes.c_int64),
+        ("kv_stride_b", ctypes.c_int64), ("kv_stride_h", ctypes.c_int64), ("kv_stride_s", ctypes.c_int64),
+        ("dtype", ctypes.c_int32), ("is_causal", ctypes.c_int32), ("softmax_scale", ctypes.c_float),
+        ("out_fp32", ctypes.c_int32), ("num_splits", ctypes.c_int32),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t), ("stream", ctypes.c_void_p),
+    ]
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -49,6 +64,12 @@ def lib():
         L.tfa_fwd_ex.restype = ci
         L.tfa_fwd_multi.argtypes = [ctypes.POINTER(FwdArgs), ctypes.POINTER(ctypes.c_void_p), ci]
         L.tfa_fwd_multi.restype = ci
+        L.tfa_attn_fwd.argtypes = [ctypes.POINTER(AttnArgs)]
+        L.tfa_attn_fwd.restype = ci
+        L.tfa_attn_num_splits.argtypes = [ctypes.POINTER(AttnArgs)]
+        L.tfa_attn_num_splits.restype = ci
+        L.tfa_attn_workspace_bytes.argtypes = [ctypes.POINTER(AttnArgs), ci]
+        L.tfa_attn_workspace_bytes.restype = ctypes.c_size_t
         L.tfa_fwd_host.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, ci]
         L.tfa_fwd_host.restype = ci
         L.tfa_host_release.restype = None
@@ -108,6 +129,32 @@ def fwd(q, k, v, is_causal, softmax_scale, out_fp32=False, layout="bhsd", stream
     a = FwdArgs(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), B, H, S, D, sb, sh, ss,
                 _dtype_code(q), int(bool(is_causal)), float(softmax_scale), int(bool(out_fp32)), st)
     check(lib().tfa_fwd_ex(ctypes.byref(a)))
+    return out, lse
+
+
+def attn_fwd(q, k, v, is_causal, softmax_scale, num_splits=1, out_fp32=False, stream=None, return_splits=False):
+    """Generalised problem through tfa_attn_fwd(): q (B,Hq,Sq,D), k/v (B,Hkv,Sk,D) contiguous device tensors,
+    bottom-right causal mask, optional split-KV (num_splits: 1 none, n > 1 as asked, 0 library heuristic)."""
+    import torch
+    assert q.is_cuda and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    B, Hq, Sq, D = q.shape
+    _, Hkv, Sk, _ = k.shape
+    out = torch.empty(q.shape, dtype=torch.float32 if out_fp32 else q.dtype, device=q.device)
+    lse = torch.empty((B, Hq, Sq), dtype=torch.float32, device=q.device)
+    st = stream if stream is not None else torch.cuda.current_stream(q.device).cuda_stream
+    a = AttnArgs(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), B, Hq, Hkv, Sq, Sk, D,
+                 Hq * Sq * D, Sq * D, D, Hkv * Sk * D, Sk * D, D, _dtype_code(q), int(bool(is_causal)),
+                 float(softmax_scale), int(bool(out_fp32)), int(num_splits), None, 0, st)
+    L = lib()
+    n = int(L.tfa_attn_num_splits(ctypes.byref(a)))
+    ws = None
+    if n > 1:
+        need = int(L.tfa_attn_workspace_bytes(ctypes.byref(a), n))
+        ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=q.device)
+        a.workspace, a.workspace_bytes, a.num_splits = ws.data_ptr(), need, n
+    check(L.tfa_attn_fwd(ctypes.byref(a)))
+    if return_splits:
+        return out, lse, n
     return out, lse
 
 
