@@ -16,11 +16,27 @@ L.tfa_microbench_pipe.argtypes = [ci, ci, ci, ci, vp, vp, vp]
 L.tfa_microbench_pipe.restype = ci
 L.tfa_microbench_umma.argtypes = [ci, ci, ci, ci, ci, vp, vp]
 L.tfa_microbench_umma.restype = ci
+L.tfa_microbench_softmax.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp, vp]
+L.tfa_microbench_softmax.restype = ci
 NAMES = ["MUFU.EX2", "FFMA", "FFMA2", "FADD2", "FMNMX3", "F2FP.bf16x2", "ex2_poly2(pair)", "FFMA2+2xMUFU(pair)"]
 sink = torch.zeros(4, device="cuda")
 cyc = torch.zeros(1024, dtype=torch.int64, device="cuda")
 out = {}
 iters = 2000
+if "softmax" in sys.argv[1:]:
+    # exponential phase of the softmax in isolation: cycles per 128-element row per warp
+    inp = torch.empty(4100, device="cuda").normal_(0, 2.0)
+    inp[4096], inp[4097] = 0.1275, -0.3
+    for emu in (0, 1, 2, 3):
+        for cw, sw in ((4, 0), (4, 4), (4, 8), (8, 0), (8, 4)):
+            for _ in range(2):
+                tfa_ctypes.check(L.tfa_microbench_softmax(emu, 148, cw, sw, 500, inp.data_ptr(), sink.data_ptr(),
+                                                          cyc.data_ptr(), None))
+            torch.cuda.synchronize()
+            c = cyc[:148].float().median().item() / 500
+            print(f"SOFTMAX emu={emu}/8 compute warps/SMSP={cw // 4} spinning warps/SMSP={sw // 4}: "
+                  f"{c:7.1f} cycles per 128-key row per warp")
+    sys.exit(0)
 for which, name in enumerate(NAMES):
     for warps_per_smsp in (1, 2, 4):
         nthreads = 128 * warps_per_smsp

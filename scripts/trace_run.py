@@ -55,6 +55,30 @@ def main():
         last[role] = t
         print(f"{t - t0:9d}  (+{dt:6d})  {ROLE[role]:9s} {names[role].get(ev, ev)}")
     print(f"total span {evs[-1][0] - t0} cycles, {len(evs)} events")
+    # steady-state summary per softmax role: mean interval between consecutive events of one KV-tile iteration
+    for role in (0, 1):
+        seq = [(t, ev) for t, r, ev in evs if r == role]
+        iters, cur = [], {}
+        for t, ev in seq:
+            if ev == 2:
+                if cur:
+                    iters.append(cur)
+                cur = {2: t}
+            elif cur and ev in (3, 4, 5, 6):
+                cur[ev] = t
+        if cur:
+            iters.append(cur)
+        mid = [it for it in iters[2:-2] if all(e in it for e in (2, 3, 4, 5, 6))]
+        if len(mid) < 2:
+            continue
+        def mean(f):
+            xs = [f(a) for a in mid]
+            return sum(xs) / len(xs)
+        period = (mid[-1][2] - mid[0][2]) / (len(mid) - 1)
+        print(f"{ROLE[role]}: iters {len(mid)}  period {period:.0f}  S_ready->ld+mask+max(3) {mean(lambda a: a[3]-a[2]):.0f}  "
+              f"->rescale chk(4) {mean(lambda a: a[4]-a[3]):.0f}  ->last early hand-off(5) {mean(lambda a: a[5]-a[4]):.0f}  "
+              f"->p_full(6) {mean(lambda a: a[6]-a[5]):.0f}  softmax total {mean(lambda a: a[6]-a[2]):.0f}  "
+              f"p_full->next S_ready {period - mean(lambda a: a[6]-a[2]):.0f}")
 
 
 if __name__ == "__main__":

@@ -126,9 +126,6 @@ static_assert(kPSplitQ >= 1 && kPSplitQ <= 3, "P split point must leave work on 
 #endif
 static_assert(TFA_P_STAGES == 2 || (TFA_P_STAGES == 3 && TFA_P_SPLITQ == 2), "3-stage hand-off publishes after quarters 1, 2, 3");
 constexpr float kRescaleThresholdLog2 = 8.0f;  // lazy rescale: tolerate P up to 2^8
-#ifndef TFA_SPEC_MAX
-#define TFA_SPEC_MAX 0
-#endif
 // Of every 8 element pairs, this many use the polynomial exp2 instead of MUFU.  Measured on B200 (r01):
 // with the two-stage P hand-off, D=128 is best at 2 (+4.6%), D=64 at 3 (+20%).  -DTFA_EMU_PAIRS_PER_8=n overrides both (tuning).
 #ifdef TFA_EMU_PAIRS_PER_8
@@ -369,12 +366,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (j >= nblk[t]) continue;
           const bool last_v_user = !(t == 0 && j < nblk[1]);
           const bool has_next = (j + 1 < nblk[t]);
+#define TFA_PV(acc_, k0_, k1_, rel_, done_) issue_PV(t, sKV_addr + vslot * TILE, acc_, k0_, k1_, rel_, done_)
+#define TFA_S(rel_) issue_S(t, sKV_addr + kslot * TILE, rel_)
           // first half of P (keys 0..63 of the tile) is published early: start PV on it while the softmax
           // warpgroup is still exponentiating the second half
           mbar_wait(&p_half[t], j & 1, p.dbg, SITE_MMA_PH, j * 2 + t);
           TFA_TRACE_MMA(6 + t);
           tc_fence_after();
-          issue_PV(t, sKV_addr + vslot * TILE, j > 0, 0, 2 * kPSplitQ, nullptr, nullptr);
+          TFA_PV(j > 0, 0, 2 * kPSplitQ, nullptr, nullptr);
           if (t == 1 && j + 1 < nmax) {
             // look-ahead: V_{j+1} and K_{j+2} were requested a full iteration ago
             const int v2 = 2 * j + 3, k2 = 2 * j + 4;
@@ -386,7 +385,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #if TFA_P_STAGES == 3
           mbar_wait(&p_3q[t], j & 1, p.dbg, SITE_MMA_P3, j * 2 + t);
           tc_fence_after();
-          issue_PV(t, sKV_addr + vslot * TILE, true, 4, 6, nullptr, nullptr);
+          TFA_PV(true, 4, 6, nullptr, nullptr);
           constexpr int kTailK0 = 6;
 #else
           constexpr int kTailK0 = 2 * kPSplitQ;
@@ -394,13 +393,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait(&p_full[t], j & 1, p.dbg, SITE_MMA_P, j * 2 + t);
           TFA_TRACE_MMA(8 + t);
           tc_fence_after();
-          issue_PV(t, sKV_addr + vslot * TILE, true, kTailK0, 8, last_v_user ? &kv_empty[vslot] : nullptr,
-                   has_next ? nullptr : &o_full[t]);
+          TFA_PV(true, kTailK0, 8, last_v_user ? &kv_empty[vslot] : nullptr, has_next ? nullptr : &o_full[t]);
           if (has_next) {
             const bool last_k_user = !(t == 0 && j + 1 < nblk[1]);
-            issue_S(t, sKV_addr + kslot * TILE, last_k_user ? &kv_empty[kslot] : nullptr);
+            TFA_S(last_k_user ? &kv_empty[kslot] : nullptr);
             TFA_TRACE_MMA(12 + t);
           }
+#undef TFA_PV
+#undef TFA_S
         }
       }
     }
@@ -451,16 +451,6 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (i >= lim) sr[i] = 0xff800000u;                 // -inf
         }
         auto row_max = [&]() {
-#if TFA_SPEC_MAX
-          // off the critical path here: two chains keep the register pressure down
-          float mxa = -INFINITY, mxb = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 128; i += 4) {
-            mxa = fmax3(mxa, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
-            mxb = fmax3(mxb, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
-          }
-          return fmaxf(mxa, mxb);
-#else
           float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 128; i += 8) {
@@ -470,7 +460,6 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mxd = fmax3(mxd, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
           }
           return fmaxf(fmaxf(mxa, mxc), fmaxf(mxb, mxd));
-#endif
         };
         // lazy rescale of l and O: only when the row max moved by more than 2^8 (warp-uniform branch, rare)
         auto rescale_if_needed = [&](float mx) -> bool {
@@ -498,8 +487,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // P is produced in four quarters of 32 keys, stored to TMEM as they finish (P aliases columns [0,64) of S).
         constexpr int kEmuPairsPer8 = kEmuPairsPer8For<D>;
         const float2 c2 = make_float2(c, c);
-        auto p_quarter = [&](int qt, float2 nm2, float2& acc0, float2& acc1) {
-          uint32_t pk[16];
+        auto p_compute = [&](int qt, float2 nm2, float2& acc0, float2& acc1, uint32_t (&pk)[16]) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int pi = qt * 16 + i;
@@ -514,47 +502,16 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
             pk[i] = pack_16x2<IS_BF16>(e.x, e.y);
           }
-          tmem_st_x16(tS + qt * 16, pk);
         };
-        // hand-off: the first kPSplitQ quarters are published early (p_half) so the issuer can start PV on them
-        // while the rest is still being exponentiated, the remainder with p_full.
-        auto publish = [&](int qt) {
-          if (qt == kPSplitQ - 1 || qt == 3 || (TFA_P_STAGES == 3 && qt == 2)) {
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(qt == 3 ? &p_full[t] : (qt == kPSplitQ - 1 ? &p_half[t] : &p_3q[t]));
-            if (qt != 3) TFA_TRACE_SM(5);
-          }
+        // hand-off of everything stored so far: drain the TMEM stores, fence, one arrival per warp
+        auto hand_off = [&](uint64_t* bar) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar);
         };
 
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-#if TFA_SPEC_MAX
-        // Speculative max: quarter 0 is exponentiated against the PREVIOUS reference max while the row max of
-        // this tile is still being reduced (the two instruction streams are independent, ptxas interleaves them),
-        // which takes the max chain off the S-ready -> P-ready critical path.  The speculation fails only when
-        // the lazy-rescale threshold trips (rare): then quarter 0 is redone.  Results are bit-identical.
-        if (j == 0) m_ref = fmaxf(row_max(), -1.0e30f);     // a fully masked row (split-KV) must not give -inf
-        {
-          float2 nm2 = make_float2(-m_ref * c, -m_ref * c);
-          p_quarter(0, nm2, acc0, acc1);
-          const float mx = row_max();
-          TFA_TRACE_SM(3);
-          if (rescale_if_needed(mx)) {                         // never at j == 0 (mx == m_ref)
-            nm2 = make_float2(-m_ref * c, -m_ref * c);
-            acc0 = make_float2(0.f, 0.f);
-            acc1 = make_float2(0.f, 0.f);
-            p_quarter(0, nm2, acc0, acc1);
-          }
-          TFA_TRACE_SM(4);
-          publish(0);
-#pragma unroll
-          for (int qt = 1; qt < 4; ++qt) {
-            p_quarter(qt, nm2, acc0, acc1);
-            publish(qt);
-          }
-        }
-#else
         {
           const float mx = row_max();
           TFA_TRACE_SM(3);
@@ -564,11 +521,17 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float2 nm2 = make_float2(-m_ref * c, -m_ref * c);
 #pragma unroll
           for (int qt = 0; qt < 4; ++qt) {
-            p_quarter(qt, nm2, acc0, acc1);
-            publish(qt);
+            uint32_t pk[16];
+            p_compute(qt, nm2, acc0, acc1, pk);
+            tmem_st_x16(tS + qt * 16, pk);
+            // the first kPSplitQ quarters are handed over early (p_half) so the issuer can start PV on them while
+            // the rest is still being exponentiated, [quarter 2 with p_3q,] the remainder with p_full
+            if (qt == kPSplitQ - 1 || qt == 3 || (TFA_P_STAGES == 3 && qt == 2)) {
+              hand_off(qt == 3 ? &p_full[t] : (qt == kPSplitQ - 1 ? &p_half[t] : &p_3q[t]));
+              if (qt != 3) TFA_TRACE_SM(5);
+            }
           }
         }
-#endif
         acc0 = fadd2(acc0, acc1);
         l += acc0.x + acc0.y;
         TFA_TRACE_SM(6);

@@ -211,8 +211,9 @@ int validate(const Problem& a) {
   return 0;
 }
 
-// Split-KV decision.  `want` 0 = auto: split only when the plain grid would leave more than half of the SMs idle
-// and every split still gets >= 4 KV tiles; n > 1 = as asked, clamped so that no split is empty.
+// Split-KV decision.  `want` 0 = auto: split only when the plain grid would leave more than half of the SMs idle,
+// into as many splits as still fit one wave of CTAs (a 149th CTA would double the time), each with >= 4 KV tiles;
+// n > 1 = as asked, clamped so that no split is empty.
 int resolve_splits(const Problem& a, int want, int sms) {
   const int sq_eff = (a.causal && a.Sk < a.Sq) ? a.Sk : a.Sq;          // rows that see at least one key
   const long long items = ((static_cast<long long>(sq_eff) + 255) / 256) * a.B * a.Hq;
@@ -220,7 +221,7 @@ int resolve_splits(const Problem& a, int want, int sms) {
   int n = want;
   if (n == 0) {
     if (sms <= 0 || items * 2 > sms) return 1;
-    n = static_cast<int>((sms + items - 1) / items);
+    n = static_cast<int>(sms / items);                  // floor: items * n CTAs must fit ONE wave
     if (n > nkv / 4) n = nkv / 4;
     if (n > 32) n = 32;
   }

@@ -58,6 +58,67 @@ __global__ void pipe_bench_kernel(float* sink, long long* cycles, int iters) {
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// The exponential phase of the forward's softmax in isolation: exactly the per-row instruction mix of
+// fa_fwd_sm100.cuh (FFMA2 scale, MUFU.EX2 / polynomial exp2 in the EMU-of-8 pattern, FADD2 row sum, F2FP pack) on a
+// 128-element row held in registers, four quarters, the packed quarter stored to shared memory (stand-in for
+// tcgen05.st).  `compute_warps` warps per CTA do that; `spin_warps` more warps sit in mbar_wait() on a barrier that
+// completes only at the end, like the kernel's TMA/issuer/other-tile warps do.  Answers: how many cycles does ONE
+// warp need per 128-element row, alone and with spinning neighbours on its SMSP?
+template <int EMU>
+__global__ void __launch_bounds__(384, 1) softmax_bench_kernel(const float* in, float* sink, long long* cycles, int iters,
+                                                               int compute_warps) {
+  __shared__ uint64_t done_bar;
+  __shared__ __align__(16) uint32_t stage[12 * 32 * 16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(&done_bar, compute_warps); fence_mbar_init(); }
+  __syncthreads();
+  if (warp >= compute_warps) {                      // spinning neighbours
+    mbar_wait(&done_bar, 0, nullptr, 0, 0);
+    return;
+  }
+  uint32_t sr[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) sr[i] = __float_as_uint(in[(threadIdx.x * 128 + i) & 4095]);
+  const float c = in[4096];
+  const float2 c2 = make_float2(c, c);
+  float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+  uint32_t nmb = __float_as_uint(in[4097]);
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(nmb));   // opaque per iteration: nothing below is loop invariant
+    const float2 nm2 = make_float2(__uint_as_float(nmb), __uint_as_float(nmb));
+#pragma unroll
+    for (int qt = 0; qt < 4; ++qt) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int pi = qt * 16 + i;
+        const float2 x = ffma2(make_float2(__uint_as_float(sr[2 * pi]), __uint_as_float(sr[2 * pi + 1])), c2, nm2);
+        float2 e;
+        if (((pi * EMU) & 7) < EMU) {
+          e = ex2_poly2(x);
+        } else {
+          e.x = ex2_approx(x.x);
+          e.y = ex2_approx(x.y);
+        }
+        if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
+        pk[i] = pack_16x2<true>(e.x, e.y);
+      }
+      const uint32_t dst = smem_u32(stage + (warp * 32 + lane) * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)   // volatile: every quarter's store stays (they all hit the same 64 bytes)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + i * 16), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                     "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3]) : "memory");
+    }
+  }
+  const long long t1 = clock64();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&done_bar);
+  const float a = acc0.x + acc0.y + acc1.x + acc1.y + __uint_as_float(stage[threadIdx.x]);
+  if (a == 123.456f) sink[0] = a;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 // UMMA throughput: one CTA per SM, one thread issues `n_mma` MMAs back to back (operands = garbage smem/TMEM,
 // only timing matters), then commits and waits.  form: 0 = SS (A,B smem K-major), 1 = TS (A tmem, B smem MN-major).
 // uniform: 0 = issue inside `if (lane == 0)` (what kernel v1 did), 1 = whole warp converged + elect.sync.
@@ -134,6 +195,22 @@ int tfa_microbench_pipe(int which, int nblocks, int nthreads, int iters, float* 
   switch (which) {
 #define TFA_CASE(M) case M: pipe_bench_kernel<M><<<nblocks, nthreads, 0, s>>>(sink, cycles, iters); break;
     TFA_CASE(0) TFA_CASE(1) TFA_CASE(2) TFA_CASE(3) TFA_CASE(4) TFA_CASE(5) TFA_CASE(6) TFA_CASE(7)
+#undef TFA_CASE
+    default: return TFA_EINVAL_SHAPE;
+  }
+  tfa_internal_count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+// emu: polynomial pairs of every 8 (0..4); compute_warps + spin_warps <= 12 warps per CTA (one CTA per SM).
+int tfa_microbench_softmax(int emu, int nblocks, int compute_warps, int spin_warps, int iters, const float* in,
+                           float* sink, long long* cycles, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nthreads = (compute_warps + spin_warps) * 32;
+  if (compute_warps < 1 || nthreads > 384) return TFA_EINVAL_SHAPE;
+  switch (emu) {
+#define TFA_CASE(M) case M: softmax_bench_kernel<M><<<nblocks, nthreads, 0, s>>>(in, sink, cycles, iters, compute_warps); break;
+    TFA_CASE(0) TFA_CASE(1) TFA_CASE(2) TFA_CASE(3) TFA_CASE(4)
 #undef TFA_CASE
     default: return TFA_EINVAL_SHAPE;
   }
