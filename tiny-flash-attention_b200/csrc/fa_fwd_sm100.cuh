@@ -99,10 +99,21 @@ struct FwdCfg {
   static constexpr int SLAB_BYTES = 128 * 128;      // 128 rows x 128 B
   static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
   static constexpr int NSTAGE = (D == 128) ? 4 : 8; // K/V ring depth (tiles)
-  static constexpr int NUM_BARS = 2 + 2 * NSTAGE + 2 + 2 + 2 + 2 + 2;
+  static constexpr int NUM_BARS = 2 + 2 * NSTAGE + 2 + 2 + 2 + 2 + 2 + 2;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + 2 * TILE_BYTES + NSTAGE * TILE_BYTES + NUM_BARS * 8 + 16;
   // TMEM columns (fp32): S0 | S1 | O0 | O1 ; P_t aliases the first 64 columns of S_t
   static constexpr int TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 256 + D;
+  // D=64 leaves 128 TMEM columns unused.  -DTFA_D64_SEPARATE_P=1 (experiment, parity-tested) gives P_t its OWN 64
+  // columns there instead of aliasing S_t, so S_t(j+1) need not wait for PV_t(j) to finish reading P_t(j): the issuer
+  // launches it right after the first half of P_t(j) is handed over and the softmax warpgroup goes from tile j
+  // straight into tile j+1.  Measured on B200: 1-2 % SLOWER (0.684 vs 0.668 ms, B4 H32 S4096 D64 non-causal) -- with
+  // both warpgroups busy all the time they contend for the same sub-partitions' issue slots and XU, which is what
+  // bounds D=64 (2 x ~1350 cycles of softmax work per KV tile per sub-partition), not the S->P->S chain.  Default off.
+#ifndef TFA_D64_SEPARATE_P
+#define TFA_D64_SEPARATE_P 0
+#endif
+  static constexpr bool P_SEPARATE = (D == 64) && (TFA_D64_SEPARATE_P != 0);
+  static constexpr int TM_P0 = P_SEPARATE ? 384 : TM_S0, TM_P1 = P_SEPARATE ? 448 : TM_S1;
   static constexpr int TM_COLS = 512;
   static constexpr int THREADS = 384;
 };
@@ -110,7 +121,7 @@ struct FwdCfg {
 // watchdog call sites
 enum : uint32_t {
   SITE_LOAD_EMPTY = 1, SITE_MMA_K0 = 2, SITE_MMA_Q = 3, SITE_MMA_V = 4, SITE_MMA_P = 5, SITE_MMA_K = 6,
-  SITE_SM_S = 7, SITE_EPI_O = 8, SITE_MMA_PH = 9, SITE_MMA_P3 = 10
+  SITE_SM_S = 7, SITE_EPI_O = 8, SITE_MMA_PH = 9, SITE_MMA_P3 = 10, SITE_SM_PV = 11
 };
 
 // P hand-off point: the first kPSplitQ of 4 key-quarters go to the issuer early (PV k-steps [0, 2*kPSplitQ)).
@@ -166,7 +177,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* o_full = p_full + 2;            // [2]
   uint64_t* p_half = o_full + 2;            // [2]
   uint64_t* p_3q = p_half + 2;              // [2]  (TFA_P_STAGES == 3 only)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_3q + 2);
+  uint64_t* pv_done = p_3q + 2;             // [2]  (P_SEPARATE only: PV_t(j) finished, P_t / O_t may be rewritten)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -210,6 +222,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&p_full[t], 4);      // one arrival per softmax warp
       mbar_init(&p_half[t], 4);
       mbar_init(&p_3q[t], 4);
+      mbar_init(&pv_done[t], 1);
       mbar_init(&o_full[t], 1);
     }
     fence_mbar_init();
@@ -313,11 +326,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
       };
       // O_t += P_t V for k-steps [k0, k1): 16 kv rows per step = 2048 B (128 units); LBO = next 64-column slab
-      auto issue_PV = [&](int t, uint32_t v_addr, bool acc, int k0, int k1, uint64_t* release_bar, uint64_t* done_bar) {
+      auto issue_PV = [&](int t, uint32_t v_addr, bool acc, int k0, int k1, uint64_t* release_bar, uint64_t* done_bar,
+                          uint64_t* done_bar2 = nullptr) {
         const uint32_t v_lo = umma_desc_lo(v_addr, C::SLAB_BYTES);
         const uint32_t tb = opaque(tmem_base);
         const uint32_t d_tmem = tb + (t == 0 ? C::TM_O0 : C::TM_O1);
-        const uint32_t p_tmem = tb + (t == 0 ? C::TM_S0 : C::TM_S1);
+        const uint32_t p_tmem = tb + (t == 0 ? C::TM_P0 : C::TM_P1);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < C::BN / 16; ++k) {
@@ -325,6 +339,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           if (release_bar != nullptr) umma_commit(release_bar);
           if (done_bar != nullptr) umma_commit(done_bar);
+          if (done_bar2 != nullptr) umma_commit(done_bar2);
         }
         __syncwarp();
       };
@@ -366,7 +381,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (j >= nblk[t]) continue;
           const bool last_v_user = !(t == 0 && j < nblk[1]);
           const bool has_next = (j + 1 < nblk[t]);
-#define TFA_PV(acc_, k0_, k1_, rel_, done_) issue_PV(t, sKV_addr + vslot * TILE, acc_, k0_, k1_, rel_, done_)
+#define TFA_PV(acc_, k0_, k1_, rel_, done_, ...) \
+  issue_PV(t, sKV_addr + vslot * TILE, acc_, k0_, k1_, rel_, done_, ##__VA_ARGS__)
 #define TFA_S(rel_) issue_S(t, sKV_addr + kslot * TILE, rel_)
           // first half of P (keys 0..63 of the tile) is published early: start PV on it while the softmax
           // warpgroup is still exponentiating the second half
@@ -382,6 +398,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             kv_confirmed = true;
             TFA_TRACE_MMA(11);
           }
+          const bool last_k_user = !(t == 0 && j + 1 < nblk[1]);
+          if (C::P_SEPARATE && has_next) {
+            // P_t has its own TMEM columns: S_t(j+1) may overwrite S_t now (the softmax warpgroup holds row j in
+            // registers since before it handed over the first half of P)
+            TFA_S(last_k_user ? &kv_empty[kslot] : nullptr);
+            TFA_TRACE_MMA(12 + t);
+          }
 #if TFA_P_STAGES == 3
           mbar_wait(&p_3q[t], j & 1, p.dbg, SITE_MMA_P3, j * 2 + t);
           tc_fence_after();
@@ -393,9 +416,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait(&p_full[t], j & 1, p.dbg, SITE_MMA_P, j * 2 + t);
           TFA_TRACE_MMA(8 + t);
           tc_fence_after();
-          TFA_PV(true, kTailK0, 8, last_v_user ? &kv_empty[vslot] : nullptr, has_next ? nullptr : &o_full[t]);
-          if (has_next) {
-            const bool last_k_user = !(t == 0 && j + 1 < nblk[1]);
+          TFA_PV(true, kTailK0, 8, last_v_user ? &kv_empty[vslot] : nullptr, has_next ? nullptr : &o_full[t],
+                 (C::P_SEPARATE && has_next) ? &pv_done[t] : nullptr);
+          if (!C::P_SEPARATE && has_next) {
             TFA_S(last_k_user ? &kv_empty[kslot] : nullptr);
             TFA_TRACE_MMA(12 + t);
           }
@@ -418,6 +441,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t tmem_base = read_tmem_base();
       const uint32_t tS = tmem_base + lane_base + (t == 0 ? C::TM_S0 : C::TM_S1);
       const uint32_t tO = tmem_base + lane_base + (t == 0 ? C::TM_O0 : C::TM_O1);
+      const uint32_t tP = tmem_base + lane_base + (t == 0 ? C::TM_P0 : C::TM_P1);   // == tS unless P_SEPARATE
       const float c = p.scale_log2;
 
       TFA_TRACE_DECL(t)
@@ -515,15 +539,24 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         {
           const float mx = row_max();
           TFA_TRACE_SM(3);
-          if (j == 0) m_ref = fmaxf(mx, -1.0e30f);            // a fully masked row (split-KV) must not give -inf
-          else rescale_if_needed(mx);
+          if (j == 0) {
+            m_ref = fmaxf(mx, -1.0e30f);                      // a fully masked row (split-KV) must not give -inf
+          } else {
+            if (C::P_SEPARATE) {
+              // S_t(j) was issued BEFORE the tail of PV_t(j-1), so s_full no longer implies that PV_t(j-1) is done:
+              // wait for its own commit before O_t is rescaled or P_t overwritten (normally long satisfied)
+              mbar_wait(&pv_done[t], (j - 1) & 1, p.dbg, SITE_SM_PV, j * 2 + t);
+              tc_fence_after();
+            }
+            rescale_if_needed(mx);
+          }
           TFA_TRACE_SM(4);
           const float2 nm2 = make_float2(-m_ref * c, -m_ref * c);
 #pragma unroll
           for (int qt = 0; qt < 4; ++qt) {
             uint32_t pk[16];
             p_compute(qt, nm2, acc0, acc1, pk);
-            tmem_st_x16(tS + qt * 16, pk);
+            tmem_st_x16(tP + qt * 16, pk);
             // the first kPSplitQ quarters are handed over early (p_half) so the issuer can start PV on them while
             // the rest is still being exponentiated, [quarter 2 with p_3q,] the remainder with p_full
             if (qt == kPSplitQ - 1 || qt == 3 || (TFA_P_STAGES == 3 && qt == 2)) {
