@@ -529,7 +529,7 @@ def run_ours(args):
                      "flops_per_launch": F_launch, "launches_per_step_per_rank": launches_per_step,
                      "traffic": PROFILED_DRAM_BYTES_PER_HEAD * (Bl * H) / launches_per_step,
                      "traffic_source": "profiles/r01_final_cfg5shard_ncu_full_summary.txt: dram read+write of one "
-                                       "B8 H32 launch (1060.6 MB for 1077.9 MB algorithmic), scaled by heads per launch",
+                                       "B8 H32 launch (1063.3 MB for 1077.9 MB algorithmic), scaled by heads per launch",
                      "algorithmic_bytes_per_launch": (4 * S * D * 2 + 4 * S) * (Bl * H) / launches_per_step},
         "fused_roofline": fused_roofline,
         "compute_only": {"value": compute_only_value, "unit": "TFLOP/s", "note": "kernel only, no all-gather"},
@@ -551,7 +551,7 @@ def q_bytes(B, H, S, D):
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel from the committed
 # `ncu --set full` capture (profiles/r01_final_cfg5shard_ncu_full_summary.txt: 805.39 MB + 255.18 MB for
 # B=8 x H=32 heads of S=4096, D=128), expressed per (batch*head) problem.
-PROFILED_DRAM_BYTES_PER_HEAD = (805.391872e6 + 255.183104e6) / 256.0
+PROFILED_DRAM_BYTES_PER_HEAD = (805.366016e6 + 257.943040e6) / 256.0
 
 
 def emit(line: dict) -> None:

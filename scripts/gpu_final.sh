@@ -13,3 +13,9 @@ for k,v in d["configs"].items(): print("  ", k, "%.3f ms %.0f TFLOP/s frac %.3f 
 PY
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fa_fwd_sm100 -s 3 -c 1 -f -o gpurun_out/prof_cfg5shard python scripts/quick_time.py '[[8,32,4096,128,true]]' > gpurun_out/ncu_full.log 2>&1; echo "ncu_full rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-extras > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu_launches rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'splitkv_combine|fa_fwd_sm100' -s 6 -c 2 -f -o gpurun_out/prof_splitkv python scripts/splitkv_case.py 0 > gpurun_out/ncu_splitkv.log 2>&1; echo "ncu_splitkv rc=$?"
+python - <<'PY'
+import json
+d=json.load(open("gpurun_out/bench_n1.json"))
+print(json.dumps(d.get("next_rows"), indent=1))
+PY
