@@ -23,6 +23,20 @@ sink = torch.zeros(4, device="cuda")
 cyc = torch.zeros(1024, dtype=torch.int64, device="cuda")
 out = {}
 iters = 2000
+if "umma2" in sys.argv[1:]:
+    # 2-CTA (cta_group::2) MMA: cycles per M=256 instruction of a CTA pair, all 74 pairs issuing
+    L.tfa_microbench_umma2.argtypes = [ci, ci, ci, ci, vp, vp]
+    L.tfa_microbench_umma2.restype = ci
+    for (N, form, fname) in ((128, 0, "SS M=256 N=128 (QK^T, two Q tiles' rows)"), (128, 1, "TS M=256 N=128 (PV D=128)"),
+                             (64, 1, "TS M=256 N=64 (PV D=64)"), (256, 0, "SS M=256 N=256")):
+        n_mma = 4096
+        for _ in range(2):
+            tfa_ctypes.check(L.tfa_microbench_umma2(148, n_mma, N, form, cyc.data_ptr(), None))
+        torch.cuda.synchronize()
+        c = cyc[:74].float().median().item() / n_mma
+        flops = 2 * 256 * N * 16
+        print(f"UMMA2 {fname:40s}: {c:7.2f} SM-cycles per MMA ({flops / c / 2:7.0f} flop/clk/SM)")
+    sys.exit(0)
 if "softmax" in sys.argv[1:]:
     # exponential phase of the softmax in isolation: cycles per 128-element row per warp
     inp = torch.empty(4100, device="cuda").normal_(0, 2.0)

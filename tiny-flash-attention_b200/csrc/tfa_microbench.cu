@@ -185,6 +185,77 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(long long* cycles, i
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
 }
 
+// tcgen05.mma.cta_group::2 throughput (design input for a 2-CTA forward): a cluster of two CTAs on one TPC forms an
+// M=256 x N MMA; each CTA holds its own 128 rows of A and HALF of B, so per SM the shared-memory operand traffic of
+// the SS form drops from 8 KB to 6 KB per K=16 step -- the 1-CTA SS form is paced by exactly that traffic (102
+// cycles against 64-73 for the TS form).  form 0 = SS, 1 = TS (A from TMEM).  Operands are garbage; timing only.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma2_bench_kernel(long long* cycles, int n_mma, int N, int form) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 65536);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t cta_rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  for (int i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) {   // one warp of EACH CTA of the pair, same slot offset in both
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tb = *slot;
+  if (warp == 1) {
+    long long t0 = 0;
+    if (cta_rank == 0) {           // the leader CTA issues for the pair
+      const uint32_t idesc = umma_idesc_f16(1, 256, N, 0, form == 0 ? 0 : 1);
+      const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 32768);
+      t0 = clock64();
+      for (int i = 0; i < n_mma; i += 8) {
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (form == 0) {
+              const uint32_t off = (k / 4) * 16384 + (k % 4) * 32;
+              const uint64_t ad = umma_smem_desc(a_addr + off, 16, 1024), bd = umma_smem_desc(b_addr + off, 16, 1024);
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                           "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tb), "l"(ad), "l"(bd),
+                           "r"(idesc), "r"(1u) : "memory");
+            } else {
+              const uint64_t bd = umma_smem_desc(b_addr + k * 2048, 16384, 1024);
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                           "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tb + 256), "r"(tb + k * 8),
+                           "l"(bd), "r"(idesc), "r"(1u) : "memory");
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        const uint16_t mask = 3;
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, 0, nullptr, 0, 0);          // both CTAs: the multicast commit arrives on each CTA's barrier
+    if (cta_rank == 0 && lane == 0) cycles[blockIdx.x / 2] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -214,6 +285,21 @@ int tfa_microbench_softmax(int emu, int nblocks, int compute_warps, int spin_war
 #undef TFA_CASE
     default: return TFA_EINVAL_SHAPE;
   }
+  tfa_internal_count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+// nblocks must be even (clusters of 2); writes one cycle count per PAIR.
+int tfa_microbench_umma2(int nblocks, int n_mma, int N, int form, long long* cycles, void* stream) {
+  const int smem = 65536 + 1024 + 64;
+  static bool attr = false;
+  if (nblocks & 1) return TFA_EINVAL_SHAPE;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(umma2_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  umma2_bench_kernel<<<nblocks, 128, smem, static_cast<cudaStream_t>(stream)>>>(cycles, n_mma, N, form);
   tfa_internal_count_launch();
   return static_cast<int>(cudaGetLastError());
 }
