@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("TFA_LIB", os.path.join(HERE, "libtfa_b200.so"))   # T
 
 TFA_BF16, TFA_FP16 = 0, 1
 _LIB = None
+_WORKSPACES = {}     # (device, stream) -> last split-KV workspace, see attn_fwd()
 
 
 class TfaError(RuntimeError):
@@ -147,11 +148,13 @@ def attn_fwd(q, k, v, is_causal, softmax_scale, num_splits=1, out_fp32=False, st
                  float(softmax_scale), int(bool(out_fp32)), int(num_splits), None, 0, st)
     L = lib()
     n = int(L.tfa_attn_num_splits(ctypes.byref(a)))
-    ws = None
     if n > 1:
         need = int(L.tfa_attn_workspace_bytes(ctypes.byref(a), n))
         ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=q.device)
         a.workspace, a.workspace_bytes, a.num_splits = ws.data_ptr(), need, n
+        # the launch is asynchronous: keep the workspace alive until the next call on the same stream (which is
+        # ordered behind this one) instead of handing it back to the allocator while the kernels may still run
+        _WORKSPACES[(q.device.index, int(st))] = ws
     check(L.tfa_attn_fwd(ctypes.byref(a)))
     if return_splits:
         return out, lse, n
