@@ -509,6 +509,10 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             cpu_baseline = {"error": repr(e)}
 
+    long_region = args.steps * launches_per_step * k_mean >= 0.020
+    roof_peak = peak_sus if long_region else peak
+    roof_peak_name = ("bf16_tflops_sustained (kernel timed inside a %.0f ms back-to-back region)" % (
+        args.steps * launches_per_step * k_mean * 1e3)) if long_region else "bf16_tflops (burst; kernel timed alone)"
     line = {
         "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -522,8 +526,13 @@ def run_ours(args):
         "clocks": clk.summary(),
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "frac_of_sustained_peak": achieved / peak_sus, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}, burst)",
+        # denominator: the kernel is timed INSIDE the timed region (args.steps launches back to back, tens of ms of
+        # continuous tensor work), so the sustained cuBLAS figure is the comparable one; the burst figure (a kernel
+        # timed alone) is kept beside it and is what `configs` / DESIGN.md's per-kernel tables use
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": roof_peak, "unit": "TFLOP/s",
+                     "frac": achieved / roof_peak,
+                     "frac_of_burst_peak": achieved / peak, "frac_of_sustained_peak": achieved / peak_sus,
+                     "peak_source": f"MEASURED_PEAKS.json ({peak_src}): " + roof_peak_name,
                      "kernel": "fa_fwd_sm100_kernel<128,causal,bf16>", "kernel_ms_mean": k_mean * 1e3, "kernel_ms_min": k_min * 1e3,
                      "timing": "CUDA events around each launch inside the timed region",
                      "flops_per_launch": F_launch, "launches_per_step_per_rank": launches_per_step,
