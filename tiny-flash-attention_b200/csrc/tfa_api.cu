@@ -10,6 +10,7 @@
 #include "../../include/tfa_b200.h"
 #include "fa_fwd_sm100.cuh"
 #include "fa_fwd_sm100_persistent.cuh"
+#include "fa_fwd_sm100_colsplit.cuh"
 #include "fa_splitkv_combine.cuh"
 
 #include <cuda_runtime.h>
@@ -111,12 +112,13 @@ int num_sms() {
 }
 
 // TFA_KERNEL=persistent selects the persistent variant (fa_fwd_sm100_persistent.cuh); default = one CTA per item.
-// 0 = default (one CTA per work item), 1 = persistent
+// 0 = default (one CTA per work item), 1 = persistent, 2 = column-split softmax (experimental)
 int kernel_variant() {
   static int v = [] {
     const char* e = std::getenv("TFA_KERNEL");
     if (e == nullptr) return 0;
     if (std::strcmp(e, "persistent") == 0) return 1;
+    if (std::strcmp(e, "colsplit") == 0) return 2;     // experimental, see fa_fwd_sm100_colsplit.cuh
     return 0;
   }();
   return v;
@@ -134,6 +136,9 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_persistent_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, tfa::PFwdCfg<D>::SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_colsplit_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, tfa::CsCfg<D>::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
   const bool plain = p.nsplit == 1 && p.kv_group == 1 && p.Sk == p.S;   // the persistent variant is square/MHA only
@@ -146,6 +151,9 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
     const int nblocks = static_cast<int>(nitems < sms ? nitems : sms);       // one CTA per SM
     tfa::fa_fwd_sm100_persistent_kernel<D, CAUSAL, IS_BF16, OUT_F32>
         <<<nblocks, tfa::PFwdCfg<D>::THREADS, tfa::PFwdCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  } else if (kernel_variant() == 2) {
+    tfa::fa_fwd_sm100_colsplit_kernel<D, CAUSAL, IS_BF16, OUT_F32>
+        <<<static_cast<int>(nitems), tfa::CsCfg<D>::THREADS, tfa::CsCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   } else {
     tfa::fa_fwd_sm100_kernel<D, CAUSAL, IS_BF16, OUT_F32>
         <<<static_cast<int>(nitems), FwdCfg<D>::THREADS, FwdCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
