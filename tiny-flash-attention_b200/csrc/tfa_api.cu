@@ -136,9 +136,6 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_persistent_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, tfa::PFwdCfg<D>::SMEM_BYTES);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_colsplit_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, tfa::CsCfg<D>::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
   const bool plain = p.nsplit == 1 && p.kv_group == 1 && p.Sk == p.S;   // the persistent variant is square/MHA only
@@ -152,6 +149,14 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
     tfa::fa_fwd_sm100_persistent_kernel<D, CAUSAL, IS_BF16, OUT_F32>
         <<<nblocks, tfa::PFwdCfg<D>::THREADS, tfa::PFwdCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   } else if (kernel_variant() == 2) {
+    // the experimental kernel sets its attribute on ITS path only: the default path never touches it
+    static std::once_flag cs_once;
+    static cudaError_t cs_err = cudaSuccess;
+    std::call_once(cs_once, [&] {
+      cs_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_colsplit_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, tfa::CsCfg<D>::SMEM_BYTES);
+    });
+    if (cs_err != cudaSuccess) return static_cast<int>(cs_err);
     tfa::fa_fwd_sm100_colsplit_kernel<D, CAUSAL, IS_BF16, OUT_F32>
         <<<static_cast<int>(nitems), tfa::CsCfg<D>::THREADS, tfa::CsCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   } else {
