@@ -105,3 +105,27 @@ def test_product_path_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "attn_oracle" not in txt, fn
+
+
+def test_split_bookkeeping_invariants(built):
+    """tfa_attn_num_splits: never an empty split, never more splits than asked, workspace grows linearly."""
+    import tfa_ctypes
+    L = tfa_ctypes.lib()
+    buf = ctypes.create_string_buffer(64)
+    base = (ctypes.addressof(buf) + 15) & ~15
+    A = tfa_ctypes.AttnArgs
+    for Sk in (1, 127, 128, 129, 1000, 4096, 65536, 100000):
+        nkv = (Sk + 127) // 128
+        for ns in (0, 1, 2, 3, 5, 8, 19, 64, 1000):
+            a = A(base, base, base, base, None, 1, 8, 8, 128, Sk, 128, 8 * 128 * 128, 128 * 128, 128, 8 * Sk * 128,
+                  Sk * 128, 128, 0, 0, 0.1, 0, ns, None, 0, None)
+            n = L.tfa_attn_num_splits(ctypes.byref(a))
+            assert 1 <= n <= max(1, nkv)
+            if ns >= 1:
+                assert n <= ns
+            if n > 1:
+                tiles = -(-nkv // n)
+                assert (n - 1) * tiles < nkv <= n * tiles          # the last split is not empty, all keys covered
+                assert L.tfa_attn_workspace_bytes(ctypes.byref(a), n) == n * 8 * 128 * 129 * 4
+            else:
+                assert L.tfa_attn_workspace_bytes(ctypes.byref(a), n) == 0
