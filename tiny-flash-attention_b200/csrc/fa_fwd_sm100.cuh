@@ -23,7 +23,8 @@
 //     polynomial on the FMA pipe to unload MUFU; O is rescaled lazily, only when the running max moved by
 //     more than 2^8 (reference: unconditional rescale every tile, flash_attention.cu:264-316);
 //   * the two Q tiles ping-pong: while softmax warpgroup 0 works on S0, the tensor core runs
-//     P1 V and the next Q1 K^T, and vice versa; P is handed over in two halves so PV starts early;
+//     P1 V and the next Q1 K^T, and vice versa; P is handed over in three stages (keys 0-63, 64-95, 96-127) so PV
+//     starts early and only two of its eight k-steps are left behind the last hand-off;
 //   * causal: KV tiles above the diagonal are skipped, only the diagonal tile is masked
 //     (reference: flash_attention.cu:536-540,576-578 with 64-wide tiles);
 //   * epilogue: O/l -> 16-bit -> swizzled smem staging -> coalesced 128-bit st.global.v4
@@ -138,7 +139,7 @@ static_assert(kPSplitQ >= 1 && kPSplitQ <= 3, "P split point must leave work on 
 static_assert(TFA_P_STAGES == 2 || (TFA_P_STAGES == 3 && TFA_P_SPLITQ == 2), "3-stage hand-off publishes after quarters 1, 2, 3");
 constexpr float kRescaleThresholdLog2 = 8.0f;  // lazy rescale: tolerate P up to 2^8
 // Of every 8 element pairs, this many use the polynomial exp2 instead of MUFU.  Measured on B200 (r01):
-// with the two-stage P hand-off, D=128 is best at 2 (+4.6%), D=64 at 3 (+20%).  -DTFA_EMU_PAIRS_PER_8=n overrides both (tuning).
+// with the staged P hand-off, D=128 is best at 2 (+4.6%; re-checked at the end of r01: 0 and 1 are 1-2.5% slower), D=64 at 3 (+20%).  -DTFA_EMU_PAIRS_PER_8=n overrides both (tuning).
 #ifdef TFA_EMU_PAIRS_PER_8
 template <int D> constexpr int kEmuPairsPer8For = TFA_EMU_PAIRS_PER_8;
 #else
