@@ -47,7 +47,11 @@ EXTRA_CONFIGS = {
     "cfg4: B=1 H=32 S=16384 D=128 bf16 causal": (1, 32, 16384, 128, True),
 }
 FALLBACK_PEAK_TFLOPS = 1590.0   # /opt/skills/guides/B200_PROFILING.md fallback
-METRIC = "attention TFLOPs/s (bf16, seqlen x head_dim) at 1/2/4/8 B200 vs roofline"
+METRIC = "attention TFLOPs/s (bf16, seqlen\u00d7head_dim) at 1/2/4/8 B200 vs roofline"   # BASELINE.json's metric, verbatim
+try:
+    METRIC = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "BASELINE.json")))["metric"]
+except Exception:  # noqa: BLE001  (file absent: keep the literal above)
+    pass
 
 
 def flops_effective(B, H, S, D):
