@@ -29,3 +29,18 @@ def test_ours_arm_refuses_to_run_without_gpu():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=300)
     assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
+
+
+def test_metric_is_baseline_json_verbatim_and_recorded_line_has_the_contract_keys():
+    """The metric string is BASELINE.json's, and the line recorded on a B200 (profiles/) carries every contract key."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.METRIC == json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_final_bench_n1.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["gpu_launches"] > 0 and d["config"]["workload"].startswith("cfg5")
