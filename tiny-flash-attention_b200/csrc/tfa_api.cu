@@ -11,6 +11,7 @@
 #include "fa_fwd_sm100.cuh"
 #include "fa_fwd_sm100_persistent.cuh"
 #include "fa_fwd_sm100_colsplit.cuh"
+#include "fa_fwd_sm100_persistent2.cuh"
 #include "fa_splitkv_combine.cuh"
 
 #include <cuda_runtime.h>
@@ -119,6 +120,7 @@ int kernel_variant() {
     if (e == nullptr) return 0;
     if (std::strcmp(e, "persistent") == 0) return 1;
     if (std::strcmp(e, "colsplit") == 0) return 2;     // experimental, see fa_fwd_sm100_colsplit.cuh
+    if (std::strcmp(e, "persistent2") == 0) return 3;  // experimental, see fa_fwd_sm100_persistent2.cuh
     return 0;
   }();
   return v;
@@ -148,6 +150,22 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
     const int nblocks = static_cast<int>(nitems < sms ? nitems : sms);       // one CTA per SM
     tfa::fa_fwd_sm100_persistent_kernel<D, CAUSAL, IS_BF16, OUT_F32>
         <<<nblocks, tfa::PFwdCfg<D>::THREADS, tfa::PFwdCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  } else if (kernel_variant() == 3 && plain) {
+    static std::once_flag p2_once;
+    static cudaError_t p2_err = cudaSuccess;
+    std::call_once(p2_once, [&] {
+      p2_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_persistent2_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, tfa::P2Cfg<D>::SMEM_BYTES);
+    });
+    if (p2_err != cudaSuccess) return static_cast<int>(p2_err);
+    cudaError_t cerr = cudaSuccess;
+    p.sched_counter = next_sched_counter(stream, &cerr);
+    if (cerr != cudaSuccess) return static_cast<int>(cerr);
+    const int sms = num_sms();
+    if (sms <= 0) return TFA_EARCH;
+    const int nblocks = static_cast<int>(nitems < sms ? nitems : sms);
+    tfa::fa_fwd_sm100_persistent2_kernel<D, CAUSAL, IS_BF16, OUT_F32>
+        <<<nblocks, tfa::P2Cfg<D>::THREADS, tfa::P2Cfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   } else if (kernel_variant() == 2) {
     // the experimental kernel sets its attribute on ITS path only: the default path never touches it
     static std::once_flag cs_once;
