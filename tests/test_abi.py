@@ -129,3 +129,35 @@ def test_split_bookkeeping_invariants(built):
                 assert L.tfa_attn_workspace_bytes(ctypes.byref(a), n) == n * 8 * 128 * 129 * 4
             else:
                 assert L.tfa_attn_workspace_bytes(ctypes.byref(a), n) == 0
+
+
+def test_launch_order_mapping_is_a_bijection(built):
+    """decode_work (csrc/fa_fwd_sm100.cuh) -- the SAME function the kernel runs, called on the host: every CTA index maps
+    to a distinct, in-range (batch*head, split, pair); inside a chunk of heads the order is heaviest pair first."""
+    import tfa_ctypes
+    L = tfa_ctypes.lib()
+    f = L.tfa_internal_decode_work
+    f.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_int * 3)]
+    f.restype = ctypes.c_int
+    out = (ctypes.c_int * 3)()
+    for BH in (1, 2, 7, 8, 9, 15, 16, 17, 33, 128, 131):
+        for npairs in (1, 2, 3, 16):
+            for nsplit in (1, 2, 5):
+                hc = min(8, BH)
+                n = BH * npairs * nsplit
+                seen = set()
+                prev = None
+                for blk in range(n):
+                    f(blk, npairs, nsplit, hc, BH, ctypes.byref(out))
+                    bh, split, pr = out[0], out[1], out[2]
+                    assert 0 <= bh < BH and 0 <= split < nsplit and 0 <= pr < npairs, (BH, npairs, nsplit, blk)
+                    assert (bh, split, pr) not in seen
+                    seen.add((bh, split, pr))
+                    chunk = bh // hc
+                    if prev is not None and prev[0] == chunk:
+                        # same chunk: (split, pair) index never decreases, pair goes heavy -> light inside a split
+                        assert (split, -pr) >= (prev[1], -prev[2])
+                    if prev is not None:
+                        assert chunk >= prev[0]                      # chunks are taken in order
+                    prev = (chunk, split, pr)
+                assert len(seen) == n

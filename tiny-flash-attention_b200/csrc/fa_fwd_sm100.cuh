@@ -7,8 +7,8 @@
 // the same FA-2 recurrence; the machine mapping is Blackwell-first:
 //
 //   * one CTA = one work item = TWO 128-row Q tiles of one (batch, head) that share every K/V tile
-//     (reference: one 64-row tile per CTA, flash_attention.cu:695-699); items are launched (b,h)-major,
-//     heaviest causal item first, so a head's K/V stay L2 resident;
+//     (reference: one 64-row tile per CTA, flash_attention.cu:695-699); items are launched in chunks of 8 heads,
+//     heaviest causal pair first across the chunk (decode_work), so K/V stay L2 resident and the grid's tail is light;
 //   * Q/K/V tiles are staged HBM -> shared memory by TMA (SWIZZLE_128B boxes of 64 x 128
 //     elements) behind mbarriers, a 4 (D=128) or 8 (D=64) deep K/V ring (reference: cp.async, single
 //     buffered, flash_attention.cu:521-525,556-565,581-590);
@@ -64,6 +64,9 @@ struct FwdParams {
   long long part_stride;      // out_f32 elements between consecutive splits
   long long lse_stride_bh;    // lse elements between consecutive (b,h)
   long long lse_part_stride;  // lse elements between consecutive splits
+  // launch order (decode_work below): heads are taken in chunks of `head_chunk`; total (batch*head) count `BH`
+  int head_chunk;
+  int BH;
   int total_items;    // npairs * B * H                         (persistent variant only)
   int* sched_counter; // zeroed before the launch; work counter  (persistent variant only)
   float scale;        // softmax_scale
@@ -156,6 +159,27 @@ constexpr uint32_t kRegsSoftmax = TFA_REGS_SOFTMAX;
 constexpr uint32_t kRegsOther = TFA_REGS_OTHER;
 static_assert((2 * kRegsSoftmax + kRegsOther) * 128 <= 384 * 168, "setmaxnreg budget exceeds the CTA register pool");
 
+// blockIdx -> work item.  CTAs are handed to SMs in blockIdx order, so this order IS the schedule.  (b,h)-major with
+// the heaviest causal item first inside each head (the round-1 order) ends the grid with one head's 32-, 30-, ... tile
+// items trickling onto idle SMs: +8 % over a balanced schedule on B4 H32 S4096 causal, +7 % on S=16384
+// (scripts/tail_model.py reproduces the measured times).  Here heads are taken in chunks of `head_chunk` (8) and
+// INSIDE a chunk the order is (split, pair)-major, head-minor: all heads' heaviest item first, then their second
+// heaviest, ... -- the tail is made of the lightest items of the last chunk, while the heads running concurrently
+// (and with them the K/V working set in L2, ~10 heads) stay what they were.  Host-callable so that a CPU test can
+// check the mapping exhaustively (tests/test_abi.py).
+__host__ __device__ __forceinline__ void decode_work(int block, int npairs, int nsplit, int head_chunk, int BH,
+                                                     int& bh, int& split, int& pr) {
+  const int per_bh = npairs * nsplit;                 // items per (batch, head)
+  const int per_chunk = head_chunk * per_bh;
+  const int chunk = block / per_chunk;
+  const int r = block - chunk * per_chunk;
+  const int g = min(head_chunk, BH - chunk * head_chunk);   // heads in this chunk (the last one may be short)
+  const int sp = r / g;                               // (split, pair) index, heaviest pair first
+  bh = chunk * head_chunk + (r - sp * g);
+  split = sp / npairs;
+  pr = npairs - 1 - (sp - split * npairs);
+}
+
 template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
 __global__ void __launch_bounds__(384, 1)
 fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -184,12 +208,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- work decode: (b,h) major, then KV split, heaviest (largest pair index) first inside a head ----
-  const int per_bh = p.npairs * p.nsplit;
-  const int bh = blockIdx.x / per_bh;
-  const int rem = blockIdx.x - bh * per_bh;
-  const int split = rem / p.npairs;
-  const int pr = p.npairs - 1 - (rem - split * p.npairs);
+  // ---- work decode (see decode_work) ----
+  int bh, split, pr;
+  decode_work(static_cast<int>(blockIdx.x), p.npairs, p.nsplit, p.head_chunk, p.BH, bh, split, pr);
   const int bidx = bh / p.H, hidx = bh % p.H;
   const int hkv = hidx / p.kv_group;                   // K/V head feeding this query head
   const int S = p.S, Sk = p.Sk;

@@ -361,6 +361,8 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
   p.npairs = static_cast<int>(npairs);
   p.nsplit = nsplit;
   p.split_tiles = split_tiles;
+  p.BH = a.B * a.Hq;
+  p.head_chunk = p.BH < 8 ? p.BH : 8;
   p.scale = a.scale;
   // scale == 0 is legal (uniform attention over the visible keys): a tiny positive exponent scale keeps
   // masked scores at -inf (0 * -inf would be NaN) while every visible score still maps to exp2(0) = 1
@@ -588,6 +590,14 @@ unsigned long long tfa_launch_count(void) { return g_launches.load(); }
 void tfa_internal_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void* tfa_internal_dbg_dev(void) { init_dbg(); return g_dbg_dev; }
 void* tfa_internal_encode_fn(void) { return reinterpret_cast<void*>(get_encode_fn()); }
+
+// development aid (not in the public header): the device's blockIdx -> work item mapping, callable on the host
+int tfa_internal_decode_work(int block, int npairs, int nsplit, int head_chunk, int BH, int* out3) {
+  int bh, split, pr;
+  tfa::decode_work(block, npairs, nsplit, head_chunk, BH, bh, split, pr);
+  out3[0] = bh; out3[1] = split; out3[2] = pr;
+  return 0;
+}
 
 // development aid (not in the public header): timeline buffer for -DTFA_TRACE variant builds
 void tfa_internal_set_trace(void* dev_buf, int block) {
