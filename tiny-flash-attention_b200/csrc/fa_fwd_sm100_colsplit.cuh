@@ -82,11 +82,8 @@ fa_fwd_sm100_colsplit_kernel(const __grid_constant__ CUtensorMap tmQ, const __gr
   const int lane = threadIdx.x & 31;
 
   // ---- work decode (identical to fa_fwd_sm100_kernel) ----
-  const int per_bh = p.npairs * p.nsplit;
-  const int bh = blockIdx.x / per_bh;
-  const int rem = blockIdx.x - bh * per_bh;
-  const int split = rem / p.npairs;
-  const int pr = p.npairs - 1 - (rem - split * p.npairs);
+  int bh, split, pr;
+  decode_work(static_cast<int>(blockIdx.x), p.npairs, p.nsplit, p.head_chunk, p.BH, bh, split, pr);
   const int bidx = bh / p.H, hidx = bh % p.H;
   const int hkv = hidx / p.kv_group;
   const int S = p.S, Sk = p.Sk;

@@ -8,12 +8,33 @@
 //   * softmax: four back-to-back TMEM loads + one wait + four max chains (was: per-chunk load/max overlap);
 //   * P produced in four quarters with three hand-offs p_half / p_3q / p_full (was: two halves, two hand-offs);
 //   * issuer: PV in three stages (k-steps 0-3, 4-5, 6-7) and K/V readiness confirmed one tile ahead inside an item;
+//   * work items are handed out in the default kernel's launch order (decode_work), not (b,h)-major;
 // Everything else (scheduler ring, producer order, hoisting rule, per-warp epilogue staging, square MHA problems only)
 // is unchanged from fa_fwd_sm100_persistent.cuh -- read that file's header for the design.
 #pragma once
 #include "fa_fwd_sm100_persistent.cuh"
 
 namespace tfa {
+
+// work item -> coordinates, in the launch order of the default kernel (decode_work: chunks of 8 heads, heaviest pair
+// first across the chunk); the atomic counter hands items out in exactly this order
+template <bool CAUSAL>
+__device__ __forceinline__ WorkItem decode_item2(int item, const FwdParams& p) {
+  WorkItem w;
+  int split, pr;
+  decode_work(item, p.npairs, 1, p.head_chunk, p.BH, w.bh, split, pr);
+  w.bidx = w.bh / p.H;
+  w.hidx = w.bh % p.H;
+  const int nkv_total = (p.S + 127) / 128;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    w.row0[t] = pr * 256 + t * 128;
+    const bool active = w.row0[t] < p.S;
+    w.nblk[t] = active ? (CAUSAL ? min(nkv_total, w.row0[t] / 128 + 1) : nkv_total) : 0;
+  }
+  w.nmax = max(w.nblk[0], w.nblk[1]);
+  return w;
+}
 
 template <int D>
 struct P2Cfg : PFwdCfg<D> {
@@ -113,7 +134,7 @@ fa_fwd_sm100_persistent2_kernel(const __grid_constant__ CUtensorMap tmQ, const _
       while (cur < total) {
         const int nxt = atomicAdd(p.sched_counter, 1);
         publish(k + 1, nxt);                   // consumers always know one item ahead
-        const WorkItem w = decode_item<CAUSAL>(cur, p);
+        const WorkItem w = decode_item2<CAUSAL>(cur, p);
         auto load_q = [&](int t) {
           if (w.nblk[t] > 0) {
             mbar_wait(bar(Q_EMPTY, t), ((qpar >> t) & 1u) ^ 1u, p.dbg, SITE_LOAD_QEMPTY);
@@ -217,7 +238,7 @@ fa_fwd_sm100_persistent2_kernel(const __grid_constant__ CUtensorMap tmQ, const _
       int cur = sched_get(0);
       // the issuer only needs the KV-tile counts of an item (never its coordinates)
       auto item_counts = [&](int item, int& n0, int& n1) {
-        const WorkItem x = decode_item<CAUSAL>(item, p);
+        const WorkItem x = decode_item2<CAUSAL>(item, p);
         n0 = x.nblk[0];
         n1 = x.nblk[1];
       };
@@ -339,7 +360,7 @@ fa_fwd_sm100_persistent2_kernel(const __grid_constant__ CUtensorMap tmQ, const _
     for (int k = 0;; ++k) {
       const int item = sched_get(k);
       if (item >= total) break;
-      const WorkItem w = decode_item<CAUSAL>(item, p);
+      const WorkItem w = decode_item2<CAUSAL>(item, p);
       const int n = (t == 0) ? w.nblk[0] : w.nblk[1];
       if (n == 0) continue;
       const int trow0 = (t == 0) ? w.row0[0] : w.row0[1];
