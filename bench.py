@@ -400,7 +400,8 @@ def run_ours(args):
             tt = torch.tensor([te], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             te = float(tt.item())
-        same = bool(torch.equal(hout[0, 0], out[0, 0].cpu()))
+        dev_head = (fused.buf[lo, 0] if fused is not None else out[0, 0])      # fused mode never writes `out`
+        same = bool(torch.equal(hout[0, 0], dev_head.cpu()))
         e2e = {"value": F_job / te / 1e12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": int(3 * q.numel() * 2 * world), "d2h_bytes_per_step": int((out.numel() * 2 + lse.numel() * 4) * world),
                "ms_per_step": te * 1e3, "api": "tfa_fwd_host (C ABI, pinned host buffers, 8 chunks on 4 streams)",
@@ -408,30 +409,57 @@ def run_ours(args):
         tfa.lib().tfa_host_release()
         del hq, hk, hv, hout, hlse
 
+    # ---- parity: the result every rank holds after a step, against fp32 torch, on heads picked to cover the launch
+    #      order's first and last chunk and (N>1) a head computed by ANOTHER rank and delivered by the exchange ----
+    result = fused.buf if fused is not None else (o_full if world > 1 else out)      # (B,H,S,D) at N>1, local at N=1
+    peer_head = None
+    if world > 1:
+        src = 1                                                  # rank 1's first (batch, head): inputs live there
+        pq = torch.empty(3, S, D, dtype=torch.bfloat16, device=dev)
+        if rank == src:
+            pq.copy_(torch.stack([q[0, 0], k[0, 0], v[0, 0]]))
+        dist.broadcast(pq, src)
+        peer_head = (pq[0], pq[1], pq[2], shard_batch(B, src, world)[0], 0)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
 
-    # ---- rank 0 extras: parity spot check, other configs, cpu baseline ----
-    parity = None
-    try:
-        b0, h0 = 0, 0
-        qf, kf, vf = q[b0, h0].float(), k[b0, h0].float(), v[b0, h0].float()
+    def check_head(qh, kh, vh, got, label):
         old = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False
-        s_ = (qf @ kf.t()) * scale
-        s_.masked_fill_(torch.ones(S, S, device=dev, dtype=torch.bool).triu_(1), float("-inf"))
-        want = torch.softmax(s_, dim=-1) @ vf
+        s_ = (qh.float() @ kh.float().t()) * scale
+        if causal:
+            s_.masked_fill_(torch.ones(S, S, device=dev, dtype=torch.bool).triu_(1), float("-inf"))
+        want = torch.softmax(s_, dim=-1) @ vh.float()
         torch.backends.cuda.matmul.allow_tf32 = old
-        diff = (out[b0, h0].float() - want).abs()
+        diff = (got.float() - want).abs()
         ok = diff <= 1e-3 + 1e-3 * want.abs()
-        parity = {"vs": "fp32 torch softmax(scale QK^T)V, head (0,0)", "max_abs_err": float(diff.max()),
-                  "pass_frac_rtol1e-3_atol1e-3": float(ok.float().mean())}
-        del s_, want
+        return {"head": label, "max_abs_err": float(diff.max()), "pass_frac_rtol1e-3_atol1e-3": float(ok.float().mean())}
+
+    parity = None
+    parity_ok = True
+    try:
+        gb = lo if world > 1 else 0                              # global batch index of this rank's first batch in `result`
+        heads = [check_head(q[0, 0], k[0, 0], v[0, 0], result[gb, 0], f"first local (b={gb},h=0)"),
+                 check_head(q[Bl - 1, H - 1], k[Bl - 1, H - 1], v[Bl - 1, H - 1], result[gb + Bl - 1, H - 1],
+                            f"last local (b={gb + Bl - 1},h={H - 1})")]
+        if peer_head is not None:
+            pq_, pk_, pv_, pb, ph = peer_head
+            heads.append(check_head(pq_, pk_, pv_, result[pb, ph], f"computed by rank 1, delivered by the exchange (b={pb},h={ph})"))
+        worst = min(h_["pass_frac_rtol1e-3_atol1e-3"] for h_ in heads)
+        parity = {"vs": "fp32 torch softmax(scale QK^T)V on the buffer every rank holds after a step"
+                        + (" (fused.buf: written by the kernel epilogues of all ranks)" if fused is not None else ""),
+                  "max_abs_err": max(h_["max_abs_err"] for h_ in heads), "pass_frac_rtol1e-3_atol1e-3": worst,
+                  "heads": heads,
+                  "note": "misses are bf16 output rounding on early causal rows (half an ulp at |O|>=0.5 exceeds 1e-3); "
+                          "the fp32-output build passes strictly (tests/test_fwd_parity.py)"}
+        parity_ok = worst >= 0.999
     except Exception as e:  # noqa: BLE001
         parity = {"error": repr(e)}
+        parity_ok = False
 
     configs = {}
     if world == 1 and not args.no_extras:
@@ -505,18 +533,38 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         try:
             fn, kind, cores = cpu_reference_runner()
-            heads, _ = pick_sample_heads(fn, S, D, causal, scale, target_s=12.0, max_heads=B * H)
+            heads, _ = pick_sample_heads(fn, S, D, causal, scale, target_s=10.0, max_heads=B * H)
             ts = time_cpu_sample(fn, heads, S, D, causal, scale, 1, 0)
             cpu_baseline = {"value": flops_effective(1, heads, S, D) / ts[0] / 1e12, "unit": "TFLOP/s", "cores": cores,
                             "kind": kind, "sample": f"{heads} of {B * H} (batch*head) problems of the workload, fp32 "
                                                     f"copies of the same-distribution inputs, 1 pass ({ts[0]:.1f} s)"}
+            # the same C++ CPU path on BASELINE configs 2-4 (bounded head samples, ~2 s each) ...
+            others = {}
+            for name, (b_, h_, s_, d_, c_) in EXTRA_CONFIGS.items():
+                hs, _ = pick_sample_heads(fn, s_, d_, c_, 1.0 / math.sqrt(d_), target_s=2.0, max_heads=b_ * h_)
+                t1 = time_cpu_sample(fn, hs, s_, d_, c_, 1.0 / math.sqrt(d_), 1, 0)[0]
+                others[name] = {"tflops": flops_effective(1, hs, s_, d_) / t1 / 1e12, "heads_sampled": hs, "of": b_ * h_,
+                                "seconds": t1, "kind": kind, "cores": cores}
+            cpu_baseline["configs"] = others
+            # ... and the reference's naive-Python path at BASELINE config 1 (B1 H2 S128 D64 fp32, no scale, no mask)
+            cpu_baseline["naive_python_cfg1"] = time_naive_python_cfg1()
         except Exception as e:  # noqa: BLE001
             cpu_baseline = {"error": repr(e)}
 
-    long_region = args.steps * launches_per_step * k_mean >= 0.020
-    roof_peak = peak_sus if long_region else peak
-    roof_peak_name = ("bf16_tflops_sustained (kernel timed inside a %.0f ms back-to-back region)" % (
-        args.steps * launches_per_step * k_mean * 1e3)) if long_region else "bf16_tflops (burst; kernel timed alone)"
+    comparators = None
+    if world == 1 and not args.no_extras and not args.no_comparators:
+        comparators = run_comparators()
+
+    # denominator: the measured BURST cuBLAS figure.  The sustained figure only applies to a seconds-long region whose
+    # sampled SM clock actually sat well below max (VERDICT r01 / ADVICE r01: a 0.1-0.2 s region at ~1.9 GHz is burst).
+    clocks = clk.summary()
+    region_s = args.steps * launches_per_step * k_mean
+    sustained_applies = (region_s >= 1.0 and clocks.get("sm_mhz") and clocks.get("sm_max_mhz")
+                         and clocks["sm_mhz"] < 0.8 * clocks["sm_max_mhz"])
+    roof_peak = peak_sus if sustained_applies else peak
+    roof_peak_name = ("bf16_tflops_sustained (%.1f s region, median SM clock %.0f MHz < 0.8 max)" % (region_s, clocks["sm_mhz"])
+                      if sustained_applies else "bf16_tflops (burst)")
+    traffic, traffic_src = profiled_traffic(Bl * H / launches_per_step)
     line = {
         "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -527,44 +575,111 @@ def run_ours(args):
                        else f" + NCCL all-gather of O ({n_chunks} chunk(s))")),
                    "exchange": exchange, "exchange_check": exchange_check,
                    "flops": "2*B*H*S^2*D", "l2": "inputs (3 x %.0f MB per rank) larger than the 126 MB L2" % (q_bytes(Bl, H, S, D) / 1e6)},
-        "clocks": clk.summary(),
+        "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        # denominator: the kernel is timed INSIDE the timed region (args.steps launches back to back, tens of ms of
-        # continuous tensor work), so the sustained cuBLAS figure is the comparable one; the burst figure (a kernel
-        # timed alone) is kept beside it and is what `configs` / DESIGN.md's per-kernel tables use
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": roof_peak, "unit": "TFLOP/s",
                      "frac": achieved / roof_peak,
                      "frac_of_burst_peak": achieved / peak, "frac_of_sustained_peak": achieved / peak_sus,
                      "peak_source": f"MEASURED_PEAKS.json ({peak_src}): " + roof_peak_name,
-                     "kernel": "fa_fwd_sm100_kernel<128,causal,bf16>", "kernel_ms_mean": k_mean * 1e3, "kernel_ms_min": k_min * 1e3,
+                     "kernel": KERNEL_NAME, "kernel_ms_mean": k_mean * 1e3, "kernel_ms_min": k_min * 1e3,
                      "timing": "CUDA events around each launch inside the timed region",
                      "flops_per_launch": F_launch, "launches_per_step_per_rank": launches_per_step,
-                     "traffic": PROFILED_DRAM_BYTES_PER_HEAD * (Bl * H) / launches_per_step,
-                     "traffic_source": "profiles/r01_final_cfg5shard_ncu_full_summary.txt: dram read+write of one "
-                                       "B8 H32 launch (1063.3 MB for 1077.9 MB algorithmic), scaled by heads per launch",
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": (4 * S * D * 2 + 4 * S) * (Bl * H) / launches_per_step},
         "fused_roofline": fused_roofline,
         "compute_only": {"value": compute_only_value, "unit": "TFLOP/s", "note": "kernel only, no all-gather"},
         "cpu_baseline": cpu_baseline,
         "parity": parity,
         "configs": configs,
+        "comparators": comparators,
         "next_rows": next_rows,
     }
     emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not parity_ok:
+        sys.stderr.write("[bench] PARITY FAILED: " + json.dumps(parity) + "\n")
+        sys.exit(3)
 
 
 def q_bytes(B, H, S, D):
     return B * H * S * D * 2
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel from the committed
-# `ncu --set full` capture (profiles/r01_final_cfg5shard_ncu_full_summary.txt: 805.39 MB + 255.18 MB for
-# B=8 x H=32 heads of S=4096, D=128), expressed per (batch*head) problem.
-PROFILED_DRAM_BYTES_PER_HEAD = (805.366016e6 + 257.943040e6) / 256.0
+KERNEL_NAME = "fa_fwd_sm100_kernel<128,causal,bf16>"
+
+
+def profiled_traffic(heads_per_launch):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+    capture of the SAME kernel source (profiles/traffic.json records the capture's commit and the digest of the kernel
+    sources it was taken from); null when the kernel sources changed since -- a stale constant is worse than none."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        import hashlib
+        h = hashlib.sha256()
+        for f in rec["sources"]:
+            h.update(open(os.path.join(ROOT, f), "rb").read())
+        if h.hexdigest() != rec["sources_sha256"]:
+            return None, f"profiles/traffic.json is from commit {rec.get('commit')} and the kernel sources changed since: no traffic claim"
+        return rec["dram_bytes_per_head"] * heads_per_launch, (
+            f"{rec['capture']} (commit {rec.get('commit')}): {rec['dram_bytes_per_head'] / 1e6:.3f} MB per (batch*head) "
+            f"for {rec['algorithmic_bytes_per_head'] / 1e6:.3f} MB algorithmic, scaled by heads per launch")
+    except Exception as e:  # noqa: BLE001
+        return None, f"no profiles/traffic.json ({e!r})"
+
+
+def run_comparators(timeout_s=420):
+    """Library / reference-kernel comparators on cfg2-4 in a SUBPROCESS (scripts/comparators.py)."""
+    import subprocess
+    try:
+        env = dict(os.environ, CMP_BUDGET_S="300")
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "comparators.py")], capture_output=True, text=True,
+                           timeout=timeout_s, env=env)
+        for ln in p.stdout.splitlines():
+            if ln.startswith("CMP "):
+                return json.loads(ln[4:])
+        return {"error": "no result", "rc": p.returncode, "stderr_tail": p.stderr[-400:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
+def time_naive_python_cfg1():
+    """BASELINE config 1 (B1 H2 S128 D64 fp32, no scale, no mask) through the reference's naive-Python path
+    tiny_flash_attn.flash_attn_v2_multihead (flash_attention_py/tiny_flash_attn.py:137-196) when its unmodified copy
+    travelled with baseline/_ref (kind "reference"); else the oracle's restatement of the same block algorithm
+    (kind "port")."""
+    import torch
+    B_, H_, S_, D_ = 1, 2, 128, 64
+    g = torch.Generator().manual_seed(20)
+    q, k, v = (torch.empty(B_, H_, S_, D_).normal_(0, 0.5, generator=g) for _ in range(3))
+    F = flops_effective(B_, H_, S_, D_)
+    ref_dir = os.path.join(ROOT, "baseline", "_ref", "drivers", "py")
+    if os.path.exists(os.path.join(ref_dir, "tiny_flash_attn.py")):
+        sys.path.insert(0, ref_dir)
+        try:
+            import tiny_flash_attn as tfa_py
+            torch.set_num_threads(1)
+            fn = lambda: tfa_py.flash_attn_v2_multihead(q, k, v, device="cpu", BLOCK_M=4)
+            kind, what = "reference", "tiny_flash_attn.flash_attn_v2_multihead(device='cpu', BLOCK_M=4), unmodified copy"
+        finally:
+            sys.path.remove(ref_dir)
+    else:
+        from oracle import oracle as orc
+        fn = lambda: orc.flash_v2_blocks(q.numpy(), k.numpy(), v.numpy(), 4)
+        kind, what = "port", "oracle.flash_v2_blocks (C restatement of tiny_flash_attn.py:137-196)"
+    fn()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    t = sorted(ts)[1]
+    import torch as _t
+    _t.set_num_threads(os.cpu_count() or 1)
+    return {"tflops": F / t / 1e12, "seconds": t, "kind": kind, "cores": 1, "what": what,
+            "config": "cfg1: B=1 H=2 S=128 D=64 fp32 non-causal, scale 1"}
 
 
 def emit(line: dict) -> None:
@@ -590,6 +705,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-comparators", action="store_true")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: how O is gathered (fused peer stores in the kernel epilogue, or ncclAllGather)")
     ap.add_argument("--chunks", type=int, default=1, help="N>1: batch chunks per rank (gather/compute overlap)")

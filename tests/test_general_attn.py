@@ -194,6 +194,20 @@ def test_scale_zero_is_a_prefix_mean(tfa):
     assert torch.allclose(lse, torch.log(torch.arange(1, 201, device="cuda").float()).expand(1, 2, 200), atol=2e-4)
 
 
+def test_scale_zero_causal_split_kv(tfa):
+    """softmax_scale = 0 through causal split-KV: splits wholly above a row's diagonal must contribute weight 0
+    (LSE_s = -inf), not a partial with l = 32 * 2^-126 and a finite LSE (ex2_poly2 clamps -inf)."""
+    q, k, v = make_inputs(1, 2, 2, 256, 1024, 64, "bf16")
+    for ns in (2, 4, 8):
+        o32, lse = tfa.attn_fwd(q, k, v, True, 0.0, num_splits=ns, out_fp32=True)
+        torch.cuda.synchronize()
+        n_vis = torch.arange(1, 257, device="cuda") + (1024 - 256)               # bottom-right aligned mask
+        csum = torch.cumsum(v.float(), dim=2)
+        want = csum[:, :, n_vis - 1] / n_vis.view(1, 1, -1, 1)
+        assert torch.allclose(o32, want, rtol=2e-3, atol=2e-3), ns
+        assert torch.allclose(lse, torch.log(n_vis.float()).expand(1, 2, 256), atol=2e-4), ns
+
+
 def test_extension_general_entry(built):
     import attention_cutlass as ac
     q, k, v = make_inputs(1, 4, 2, 200, 456, 128, "bf16")

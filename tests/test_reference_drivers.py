@@ -1,0 +1,80 @@
+"""GPU: the reference's OWN drivers, byte for byte unchanged, running on top of this repo.
+
+north_star: the kernel "drops into flash_attention_cutlass/test.py and flash_attention_py/main.py unchanged".
+  * test.py (flash_attention_cutlass/test.py:43-87) imports `attention_cutlass.flash_attention_v2_cutlass`: with
+    PYTHONPATH=tiny-flash-attention_b200 that module is THIS repo's extension.  The script times the naive baseline, our
+    kernel and the official flash_attn, then asserts allclose(baseline, ours, atol=1e-2) (test.py:87); exit code 0 = pass.
+  * main.py (flash_attention_py/main.py:62-102) never imports the extension: it is the consumer of
+    the Python oracle tiny_flash_attn.py that our parity harness is pinned to, and must keep running beside us.
+The unmodified copies live under the git-ignored baseline/_ref/drivers/ (baseline/build_ref.py stages them with their
+SHA-256; /root/reference does not exist on the GPU box).  Each run's stdout is kept in gpurun_out/ for profiles/.
+
+Both scripts also call the official `flash_attn` wheel; when THAT cannot run on the device (no kernel image for sm_100)
+the scripts die in the library call before or after our part -- reported as a skip with the probe's error, because it
+says nothing about this repo."""
+import hashlib
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRV = os.path.join(ROOT, "baseline", "_ref", "drivers")
+PKG = os.path.join(ROOT, "tiny-flash-attention_b200")
+
+PROBE = r'''
+import torch
+from flash_attn import flash_attn_func
+q = torch.randn(1, 128, 2, 64, dtype=torch.float16, device="cuda")
+o = flash_attn_func(q, q, q, causal=True)
+torch.cuda.synchronize()
+print("FLASH_ATTN_OK")
+'''
+
+
+def _staged(rel):
+    path = os.path.join(DRV, rel)
+    if not os.path.exists(path):
+        pytest.skip(f"{rel} not staged (run baseline/build_ref.py where /root/reference exists)")
+    sums = dict(line.split()[::-1] for line in open(os.path.join(DRV, "SHA256SUMS")).read().splitlines())
+    assert hashlib.sha256(open(path, "rb").read()).hexdigest() == sums["drivers/" + rel], "staged copy was modified"
+    return path
+
+
+def _flash_attn_works():
+    p = subprocess.run([sys.executable, "-c", PROBE], capture_output=True, text=True, timeout=300)
+    return "FLASH_ATTN_OK" in p.stdout, (p.stderr or p.stdout)[-400:]
+
+
+def _run(path, cwd, log_name):
+    env = dict(os.environ, PYTHONPATH=PKG + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    p = subprocess.run([sys.executable, path], capture_output=True, text=True, timeout=600, env=env, cwd=cwd)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", log_name), "w") as f:
+        f.write(f"$ PYTHONPATH=tiny-flash-attention_b200 python {os.path.relpath(path, ROOT)}   (rc={p.returncode})\n")
+        f.write(p.stdout + "\n--- stderr (tail) ---\n" + p.stderr[-3000:])
+    return p
+
+
+def test_reference_test_py_runs_unchanged_on_our_extension(built):
+    path = _staged("cutlass/test.py")
+    ok, why = _flash_attn_works()
+    p = _run(path, os.path.dirname(path), "ref_test_py.log")
+    if p.returncode != 0 and not ok:
+        # the script reached (or died in) the official flash_attn call, which cannot run here; our part is covered
+        # by tests/test_drop_in_driver.py (same flow, same assert)
+        assert "flash2_cutlass_ref" in p.stdout, p.stdout[-800:] + p.stderr[-1500:]
+        pytest.skip("official flash_attn wheel cannot run on this device: " + why)
+    assert p.returncode == 0, p.stdout[-800:] + p.stderr[-2500:]
+    assert "flash2_cutlass_ref" in p.stdout and "official_ref" in p.stdout
+
+
+def test_reference_main_py_runs_unchanged(built):
+    path = _staged("py/main.py")
+    ok, why = _flash_attn_works()
+    p = _run(path, os.path.dirname(path), "ref_main_py.log")
+    if p.returncode != 0 and not ok:
+        pytest.skip("official flash_attn wheel cannot run on this device: " + why)
+    assert p.returncode == 0, p.stdout[-800:] + p.stderr[-2500:]

@@ -596,7 +596,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&o_full[t], 0, p.dbg, SITE_EPI_O, t);
       TFA_TRACE_SM(7);
       tc_fence_after();
-      // l == 0 only for a split-KV partial whose keys are all masked for this row: O = 0, LSE = -inf (weight 0)
+      // A row none of whose keys lies in this CTA's KV range (a split-KV partial wholly above the row's causal limit):
+      // the MUFU exponentials of its -inf scores are exact zeros but the polynomial ones are 2^-126 (ex2_poly2 clamps),
+      // so l would be tiny instead of 0.  Decide it analytically: O = 0, LSE = -inf (combine weight 0), also for
+      // softmax_scale == 0 where the clamped exponent scale never rescales m_ref = -1e30 away.
+      if ((CAUSAL ? min(Sk, row_g + p.causal_off + 1) : Sk) <= jb * C::BN) l = 0.f;
       const float inv_l = (l > 0.f) ? 1.0f / l : 0.f;
       const long long tile_off = static_cast<long long>(bidx) * p.o_stride_b + static_cast<long long>(hidx) * p.o_stride_h;
 

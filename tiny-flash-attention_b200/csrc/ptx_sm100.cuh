@@ -31,7 +31,7 @@ struct DebugRecord {
 };
 
 #ifndef TFA_WATCHDOG_SPINS
-#define TFA_WATCHDOG_SPINS (1u << 26)   // try_wait itself suspends ~us each; this is >> any legal wait
+#define TFA_WATCHDOG_SPINS (1u << 22)   // try_wait itself suspends ~us each: seconds, >> any legal wait (one work item is ~50 us)
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -420,7 +420,8 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
 // 2^x for two lanes WITHOUT the MUFU pipe: Cody-Waite split x = n + f (n = rint(x) via the 1.5*2^23 magic
 // add, f in [-0.5, 0.5]), degree-3 minimax polynomial for 2^f (max rel. error 7.5e-5, far below the 2^-9
 // rounding P gets anyway), then n is added into the exponent field with one LEA.
-// 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 LEA per pair; valid for x <= ~100, clamps x >= -126 (incl. -inf -> 2^-126).
+// 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 LEA per pair; valid for x <= ~100, clamps x >= -126 (incl. -inf -> ~2^-126, NOT 0:
+// callers that need an exact zero row sum for fully masked rows decide that analytically, see the kernel epilogue).
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   const float M = 12582912.f;
   x.x = fmaxf(x.x, -126.f);

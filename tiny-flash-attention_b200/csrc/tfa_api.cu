@@ -12,6 +12,7 @@
 #include "fa_fwd_sm100_persistent.cuh"
 #include "fa_fwd_sm100_colsplit.cuh"
 #include "fa_fwd_sm100_persistent2.cuh"
+#include "fa_fwd_sm100_persist.cuh"
 #include "fa_splitkv_combine.cuh"
 
 #include <cuda_runtime.h>
@@ -51,7 +52,7 @@ std::once_flag g_dbg_once;
 void init_dbg() {
   std::call_once(g_dbg_once, [] {
     void* h = nullptr;
-    if (cudaHostAlloc(&h, sizeof(DebugRecord), cudaHostAllocMapped) == cudaSuccess) {
+    if (cudaHostAlloc(&h, sizeof(DebugRecord), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
       std::memset(h, 0, sizeof(DebugRecord));
       void* d = nullptr;
       if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
@@ -65,11 +66,11 @@ void init_dbg() {
 // (B?,H?,S,D)-strided 16-bit tensor -> 4-D tiled map with dims (D, S, H, B); the kernel addresses it as
 // (x = head-dim offset, y = sequence row, z = head, w = batch).  Box = 64 x 128 elements, SWIZZLE_128B.
 int make_tmap(CUtensorMap* m, const void* base, int dtype, int D, int S, int B, int H, long long sb,
-              long long sh, long long ss) {
+              long long sh, long long ss, int box_rows = 128) {
   auto encode = get_encode_fn();
   if (!encode) return TFA_EDRIVER;
   const CUtensorMapDataType dt = (dtype == TFA_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  const cuuint32_t box[4] = {64, 128, 1, 1};
+  const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_rows), 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const cuuint64_t dims[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(H),
                               static_cast<cuuint64_t>(B)};
@@ -86,30 +87,65 @@ int make_tmap(CUtensorMap* m, const void* base, int dtype, int D, int S, int B, 
   return r == CUDA_SUCCESS ? 0 : TFA_EDRIVER;
 }
 
-// ---- work counters of the persistent kernel: a small pool, one int per in-flight launch ----
-constexpr int kNumSchedCounters = 256;
-int* g_sched_pool = nullptr;
-std::atomic<unsigned> g_sched_next{0};
-std::once_flag g_sched_once;
-int* next_sched_counter(cudaStream_t stream, cudaError_t* err) {
-  std::call_once(g_sched_once, [] {
+// ---- per-device state.  Function attributes, SM counts, work counters and workspaces belong to ONE device (context):
+//      a process that drives several GPUs (tensors on cuda:0, then cuda:1) must not reuse the first device's. ----
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
+}
+
+// ---- work counters of the persistent kernel: a small pool per device, one int per in-flight launch.  A slot is
+//      zeroed by a stream-ordered memset right before its launch and re-used only kNumSchedCounters launches later;
+//      the event recorded after each launch is waited for (host side) before the slot is handed out again, so two
+//      in-flight launches never share a counter. ----
+constexpr int kNumSchedCounters = 64;
+struct SchedPool {
+  int* base = nullptr;
+  unsigned next = 0;
+  cudaEvent_t done[kNumSchedCounters] = {};
+  bool used[kNumSchedCounters] = {};
+  std::mutex mu;
+};
+SchedPool g_sched[kMaxDevices];
+int* acquire_sched_counter(cudaStream_t stream, cudaError_t* err, int* slot_out) {
+  const int dev = current_device();
+  if (dev < 0) { *err = cudaErrorInvalidDevice; return nullptr; }
+  SchedPool& sp = g_sched[dev];
+  std::lock_guard<std::mutex> lk(sp.mu);
+  if (!sp.base) {
     void* d = nullptr;
-    if (cudaMalloc(&d, kNumSchedCounters * sizeof(int)) == cudaSuccess) g_sched_pool = static_cast<int*>(d);
-  });
-  if (!g_sched_pool) { *err = cudaErrorMemoryAllocation; return nullptr; }
-  int* c = g_sched_pool + (g_sched_next.fetch_add(1, std::memory_order_relaxed) % kNumSchedCounters);
-  *err = cudaMemsetAsync(c, 0, sizeof(int), stream);   // ordered before the kernel on the same stream
-  return c;
+    if ((*err = cudaMalloc(&d, kNumSchedCounters * sizeof(int))) != cudaSuccess) return nullptr;
+    sp.base = static_cast<int*>(d);
+  }
+  const int slot = static_cast<int>(sp.next++ % kNumSchedCounters);
+  if (sp.used[slot]) {
+    if ((*err = cudaEventSynchronize(sp.done[slot])) != cudaSuccess) return nullptr;   // normally long complete
+  } else {
+    if ((*err = cudaEventCreateWithFlags(&sp.done[slot], cudaEventDisableTiming)) != cudaSuccess) return nullptr;
+    sp.used[slot] = true;
+  }
+  *err = cudaMemsetAsync(sp.base + slot, 0, sizeof(int), stream);   // ordered before the kernel on the same stream
+  *slot_out = slot;
+  return sp.base + slot;
+}
+void release_sched_counter(int slot, cudaStream_t stream) {
+  const int dev = current_device();
+  if (dev < 0) return;
+  cudaEventRecord(g_sched[dev].done[slot], stream);
 }
 
 int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  static std::atomic<int> cache[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0) return 0;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    return v;
-  }();
-  return n;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
 }
 
 // TFA_KERNEL=persistent selects the persistent variant (fa_fwd_sm100_persistent.cuh); default = one CTA per item.
@@ -121,65 +157,61 @@ int kernel_variant() {
     if (std::strcmp(e, "persistent") == 0) return 1;
     if (std::strcmp(e, "colsplit") == 0) return 2;     // experimental, see fa_fwd_sm100_colsplit.cuh
     if (std::strcmp(e, "persistent2") == 0) return 3;  // experimental, see fa_fwd_sm100_persistent2.cuh
+    if (std::strcmp(e, "persist") == 0) return 4;      // fa_fwd_sm100_persist.cuh
     return 0;
   }();
   return v;
 }
-bool use_persistent() { return kernel_variant() == 1; }
+
+// cudaFuncSetAttribute is per device (context) and costs well under a microsecond: set it on every launch instead of
+// caching "done once" per process, which breaks the first launch on a second GPU of the same process.
+template <typename K>
+cudaError_t opt_in_smem(K kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
 
 template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
-int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, FwdParams p, long long nitems,
-                cudaStream_t stream) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<D>::SMEM_BYTES);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_persistent_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, tfa::PFwdCfg<D>::SMEM_BYTES);
-  });
-  if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
-  const bool plain = p.nsplit == 1 && p.kv_group == 1 && p.Sk == p.S;   // the persistent variant is square/MHA only
-  if (use_persistent() && plain) {
-    cudaError_t cerr = cudaSuccess;
-    p.sched_counter = next_sched_counter(stream, &cerr);
+int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const tfa::OutMaps& to, FwdParams p,
+                long long nitems, cudaStream_t stream) {
+  cudaError_t cerr = cudaSuccess;
+  const bool plain = p.nsplit == 1 && p.kv_group == 1 && p.Sk == p.S;   // the persistent variants are square/MHA only
+  const int variant = kernel_variant();
+  if (variant == 4) {
+    int slot = 0;
+    p.sched_counter = acquire_sched_counter(stream, &cerr, &slot);
     if (cerr != cudaSuccess) return static_cast<int>(cerr);
     const int sms = num_sms();
     if (sms <= 0) return TFA_EARCH;
     const int nblocks = static_cast<int>(nitems < sms ? nitems : sms);       // one CTA per SM
-    tfa::fa_fwd_sm100_persistent_kernel<D, CAUSAL, IS_BF16, OUT_F32>
-        <<<nblocks, tfa::PFwdCfg<D>::THREADS, tfa::PFwdCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
-  } else if (kernel_variant() == 3 && plain) {
-    static std::once_flag p2_once;
-    static cudaError_t p2_err = cudaSuccess;
-    std::call_once(p2_once, [&] {
-      p2_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_persistent2_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, tfa::P2Cfg<D>::SMEM_BYTES);
-    });
-    if (p2_err != cudaSuccess) return static_cast<int>(p2_err);
-    cudaError_t cerr = cudaSuccess;
-    p.sched_counter = next_sched_counter(stream, &cerr);
+    auto kern = tfa::fa_fwd_sm100_persist_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
+    if ((cerr = opt_in_smem(kern, tfa::PCfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
+    kern<<<nblocks, tfa::PCfg<D>::THREADS, tfa::PCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+    release_sched_counter(slot, stream);
+  } else if ((variant == 1 || variant == 3) && plain) {
+    int slot = 0;
+    p.sched_counter = acquire_sched_counter(stream, &cerr, &slot);
     if (cerr != cudaSuccess) return static_cast<int>(cerr);
     const int sms = num_sms();
     if (sms <= 0) return TFA_EARCH;
-    const int nblocks = static_cast<int>(nitems < sms ? nitems : sms);
-    tfa::fa_fwd_sm100_persistent2_kernel<D, CAUSAL, IS_BF16, OUT_F32>
-        <<<nblocks, tfa::P2Cfg<D>::THREADS, tfa::P2Cfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
-  } else if (kernel_variant() == 2) {
-    // the experimental kernel sets its attribute on ITS path only: the default path never touches it
-    static std::once_flag cs_once;
-    static cudaError_t cs_err = cudaSuccess;
-    std::call_once(cs_once, [&] {
-      cs_err = cudaFuncSetAttribute(tfa::fa_fwd_sm100_colsplit_kernel<D, CAUSAL, IS_BF16, OUT_F32>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, tfa::CsCfg<D>::SMEM_BYTES);
-    });
-    if (cs_err != cudaSuccess) return static_cast<int>(cs_err);
-    tfa::fa_fwd_sm100_colsplit_kernel<D, CAUSAL, IS_BF16, OUT_F32>
-        <<<static_cast<int>(nitems), tfa::CsCfg<D>::THREADS, tfa::CsCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    const int nblocks = static_cast<int>(nitems < sms ? nitems : sms);       // one CTA per SM
+    if (variant == 1) {
+      auto kern = tfa::fa_fwd_sm100_persistent_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
+      if ((cerr = opt_in_smem(kern, tfa::PFwdCfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
+      kern<<<nblocks, tfa::PFwdCfg<D>::THREADS, tfa::PFwdCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    } else {
+      auto kern = tfa::fa_fwd_sm100_persistent2_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
+      if ((cerr = opt_in_smem(kern, tfa::P2Cfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
+      kern<<<nblocks, tfa::P2Cfg<D>::THREADS, tfa::P2Cfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    }
+    release_sched_counter(slot, stream);
+  } else if (variant == 2) {
+    auto kern = tfa::fa_fwd_sm100_colsplit_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
+    if ((cerr = opt_in_smem(kern, tfa::CsCfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
+    kern<<<static_cast<int>(nitems), tfa::CsCfg<D>::THREADS, tfa::CsCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   } else {
-    tfa::fa_fwd_sm100_kernel<D, CAUSAL, IS_BF16, OUT_F32>
-        <<<static_cast<int>(nitems), FwdCfg<D>::THREADS, FwdCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    auto kern = tfa::fa_fwd_sm100_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
+    if ((cerr = opt_in_smem(kern, FwdCfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
+    kern<<<static_cast<int>(nitems), FwdCfg<D>::THREADS, FwdCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return static_cast<int>(cudaGetLastError());
@@ -187,8 +219,8 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 
 template <int D>
 int dispatch(bool causal, bool bf16, bool f32, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-             const FwdParams& p, long long nblocks, cudaStream_t s) {
-#define TFA_GO(C_, B_, F_) return launch_inst<D, C_, B_, F_>(tq, tk, tv, p, nblocks, s)
+             const tfa::OutMaps& to, const FwdParams& p, long long nblocks, cudaStream_t s) {
+#define TFA_GO(C_, B_, F_) return launch_inst<D, C_, B_, F_>(tq, tk, tv, to, p, nblocks, s)
   if (causal) {
     if (bf16) { if (f32) TFA_GO(true, true, true); else TFA_GO(true, true, false); }
     else      { if (f32) TFA_GO(true, false, true); else TFA_GO(true, false, false); }
@@ -200,13 +232,17 @@ int dispatch(bool causal, bool bf16, bool f32, const CUtensorMap& tq, const CUte
 }
 
 bool arch_ok() {
-  static int ok = [] {
-    int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
-    return major == 10 ? 1 : 0;
-  }();
-  return ok != 0;
+  static std::atomic<int> cache[kMaxDevices];    // 0 = unknown, 1 = sm_10x, 2 = something else
+  const int dev = current_device();
+  if (dev < 0) return false;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
+    v = (major == 10) ? 1 : 2;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v == 1;
 }
 
 // The problem as the launcher sees it (superset of tfa_fwd_args / tfa_attn_args).
@@ -301,7 +337,7 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
   const bool plain = (a.Sq == a.Sk) && (a.Hq == a.Hkv);
   if (n_extra > 0) {
     // fused exchange: 16-bit output of the reference-shaped problem only
-    if (n_extra > 7 || extra_dst == nullptr || f32 || kernel_variant() != 0 || !plain || a.num_splits > 1)
+    if (n_extra > 7 || extra_dst == nullptr || f32 || (kernel_variant() != 0 && kernel_variant() != 4) || !plain || a.num_splits > 1)
       return TFA_EINVAL_SHAPE;
     for (int i = 0; i < n_extra; ++i)
       if (extra_dst[i] == nullptr || (reinterpret_cast<uintptr_t>(extra_dst[i]) & 15u)) return TFA_EINVAL_PTR;
@@ -346,6 +382,15 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
   if ((rc = make_tmap(&tq, a.q, a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss))) return rc;
   if ((rc = make_tmap(&tk, a.k, a.dtype, a.D, a.Sk, a.B, a.Hkv, a.ksb, a.ksh, a.kss))) return rc;
   if ((rc = make_tmap(&tv, a.v, a.dtype, a.D, a.Sk, a.B, a.Hkv, a.ksb, a.ksh, a.kss))) return rc;
+
+  // output tensor maps of the persistent kernel's TMA-store epilogue (16-bit output only): [0] = out, [1..] = peers
+  tfa::OutMaps to;
+  std::memset(&to, 0, sizeof(to));
+  if (kernel_variant() == 4 && !f32 && nsplit == 1) {
+    if ((rc = make_tmap(&to.m[0], a.out, a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss, 32))) return rc;
+    for (int i = 0; i < n_extra; ++i)
+      if ((rc = make_tmap(&to.m[1 + i], extra_dst[i], a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss, 32))) return rc;
+  }
 
   const long long rows = static_cast<long long>(a.B) * a.Hq * a.Sq;
   float* ws_o = static_cast<float*>(a.ws);
@@ -400,8 +445,8 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
   p.total_items = static_cast<int>(nitems);
   p.sched_counter = nullptr;
   const bool kernel_f32 = f32 || nsplit > 1;
-  if (a.D == 64) rc = dispatch<64>(causal, bf16, kernel_f32, tq, tk, tv, p, nitems, stream);
-  else           rc = dispatch<128>(causal, bf16, kernel_f32, tq, tk, tv, p, nitems, stream);
+  if (a.D == 64) rc = dispatch<64>(causal, bf16, kernel_f32, tq, tk, tv, to, p, nitems, stream);
+  else           rc = dispatch<128>(causal, bf16, kernel_f32, tq, tk, tv, to, p, nitems, stream);
   if (rc) return rc;
 
   if (nsplit > 1) {
@@ -453,10 +498,11 @@ struct HostWs {
   size_t bytes = 0, lse_bytes = 0;
   std::vector<cudaStream_t> streams;
   std::vector<cudaEvent_t> events;
-} g_ws;
+};
+HostWs g_ws_all[kMaxDevices];          // one per device: the buffers and streams belong to that device's context
 std::mutex g_ws_mu;
 
-void ws_release_locked() {
+void ws_release_locked(HostWs& g_ws) {
   for (auto& p : g_ws.d) { if (p) cudaFree(p); p = nullptr; }
   if (g_ws.dlse) cudaFree(g_ws.dlse);
   g_ws.dlse = nullptr;
@@ -523,7 +569,10 @@ int tfa_fwd_host(const void* q, const void* k, const void* v, void* out, float* 
   if (B < 1 || H < 1 || S < 1) return TFA_EINVAL_SHAPE;
   if (dtype != TFA_BF16 && dtype != TFA_FP16) return TFA_EINVAL_DTYPE;
   if (!(softmax_scale >= 0.0f) || !(softmax_scale <= 3.0e38f)) return TFA_EINVAL_SCALE;
+  const int dev = current_device();
+  if (dev < 0) return static_cast<int>(cudaErrorInvalidDevice);
   std::lock_guard<std::mutex> lk(g_ws_mu);
+  HostWs& g_ws = g_ws_all[dev];
   const long long BH = static_cast<long long>(B) * H;
   const size_t head_bytes = static_cast<size_t>(S) * D * 2;
   const size_t total = head_bytes * BH;
@@ -533,7 +582,7 @@ int tfa_fwd_host(const void* q, const void* k, const void* v, void* out, float* 
     for (auto& p : g_ws.d) { if (p) cudaFree(p); p = nullptr; }
     g_ws.bytes = 0;
     for (auto& p : g_ws.d)
-      if ((e = cudaMalloc(&p, total)) != cudaSuccess) { ws_release_locked(); return static_cast<int>(e); }
+      if ((e = cudaMalloc(&p, total)) != cudaSuccess) { ws_release_locked(g_ws); return static_cast<int>(e); }
     g_ws.bytes = total;
   }
   if (g_ws.lse_bytes < lse_total) {
@@ -581,8 +630,10 @@ int tfa_fwd_host(const void* q, const void* k, const void* v, void* out, float* 
 }
 
 void tfa_host_release(void) {
+  const int dev = current_device();
+  if (dev < 0) return;
   std::lock_guard<std::mutex> lk(g_ws_mu);
-  ws_release_locked();
+  ws_release_locked(g_ws_all[dev]);
 }
 
 unsigned long long tfa_launch_count(void) { return g_launches.load(); }

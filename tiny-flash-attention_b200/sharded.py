@@ -114,6 +114,11 @@ class FusedGather:
         self.hdl.barrier()
 
     def forward(self, q_local, k_local, v_local, is_causal, scale, lse=None):
+        """Returns (gathered O, local LSE).  The gathered tensor IS the symmetric buffer: consume or copy it before the
+        next forward() -- the next call's peer stores overwrite it.  The barrier in FRONT of the launch orders those
+        stores after every rank's work queued so far (a fast rank must not overwrite a slice a slower peer is still
+        reading from the previous step); the barrier BEHIND it makes every rank's buffer complete."""
+        self.barrier()
         lse = self.launch(q_local, k_local, v_local, is_causal, scale, lse=lse)
         self.barrier()
         return self.buf, lse
