@@ -201,6 +201,31 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(index):
+    """Pin this process (and with it the first-touch placement of the pinned host buffers and the copy-issuing thread)
+    to the CPUs NVML reports as local to GPU `index`.  Under torchrun the 8 ranks otherwise all allocate their pinned
+    buffers wherever the launcher happened to run, and 7 of 8 PCIe streams cross the socket interconnect (r01: e2e at N=8
+    was 2.2x the PCIe-ideal time)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        node = None
+        try:
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            node = int(open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node").read())
+        except Exception:  # noqa: BLE001
+            pass
+        return {"bound": True, "cpus_before": before, "cpus_after": len(after), "first_cpu": after[0] if after else None,
+                "numa_node": node}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "why": repr(e)[:120]}
+
+
 def make_inputs(B, H, S, D, seed, device, dtype):
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
@@ -240,6 +265,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     tfa.lib()                                     # fail loudly if the CUDA library is missing
+    numa = bind_to_gpu_numa(local_rank)           # before any pinned allocation: first touch places it on the GPU's node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
@@ -405,7 +431,7 @@ def run_ours(args):
         e2e = {"value": F_job / te / 1e12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": int(3 * q.numel() * 2 * world), "d2h_bytes_per_step": int((out.numel() * 2 + lse.numel() * 4) * world),
                "ms_per_step": te * 1e3, "api": "tfa_fwd_host (C ABI, pinned host buffers, 8 chunks on 4 streams)",
-               "matches_device_path": same, "timer": "host wall clock around synchronous calls"}
+               "matches_device_path": same, "timer": "host wall clock around synchronous calls", "numa": numa}
         tfa.lib().tfa_host_release()
         del hq, hk, hv, hout, hlse
 

@@ -94,6 +94,18 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t smem
                "r"(smem_src), "r"(x), "r"(y), "r"(z), "r"(w)
                : "memory");
 }
+// L2 prefetch of a (64 x 128) box: the later real load of the same box is an L2 hit
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int x, int y, int z, int w) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(x), "r"(y), "r"(z), "r"(w)
+               : "memory");
+}
+// Q tiles are read exactly once, i.e. always from HBM (~2600 cycles after the buffer frees up, r01 trace), which is later
+// than the hoist point of the next item's first S.  Prefetching the NEXT item's Q tiles into L2 one item ahead turns that
+// into an L2 hit.  -DTFA_Q_PREFETCH=0 disables (A/B).
+#ifndef TFA_Q_PREFETCH
+#define TFA_Q_PREFETCH 1
+#endif
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -175,10 +187,18 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     setmaxnreg_dec<kRegsOther>();
     if (lane == 0) {
       // next non-empty work item (a split-KV item wholly above the causal diagonal has no tiles: never handed out)
+      // p.sched_counter = {next item, CTAs that ran out of work}: both are 0 at launch, and the last CTA to draw the
+      // terminator puts them back to 0 for the next launch that is handed this pair (no memset in front of each launch)
       auto fetch = [&]() -> int {
         for (;;) {
           const int i = atomicAdd(p.sched_counter, 1);
-          if (i >= total) return total;
+          if (i >= total) {
+            if (atomicAdd(p.sched_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+              p.sched_counter[0] = 0;
+              p.sched_counter[1] = 0;
+            }
+            return total;
+          }
           if (decode_pitem<CAUSAL>(i, p).nmax > 0) return i;
         }
       };
@@ -196,6 +216,17 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         const int nxt = fetch();
         publish(k + 1, nxt);                   // consumers always know one item ahead
         const PItem w = decode_pitem<CAUSAL>(cur, p);
+#if TFA_Q_PREFETCH
+        if (nxt < total) {
+          const PItem wn = decode_pitem<CAUSAL>(nxt, p);
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+            if (wn.nblk[t] > 0) {
+#pragma unroll
+              for (int sl = 0; sl < C::SLABS; ++sl) tma_prefetch_l2_4d(&tmQ, sl * 64, wn.row0[t], wn.hidx, wn.bidx);
+            }
+        }
+#endif
         auto load_q = [&](int t) {
           if (w.nblk[t] > 0) {
             mbar_wait(bar(C::Q_EMPTY, t), ((qpar >> t) & 1u) ^ 1u, p.dbg, SITE_P_QEMPTY);

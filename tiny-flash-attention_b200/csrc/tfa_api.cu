@@ -13,6 +13,7 @@
 #include "fa_fwd_sm100_colsplit.cuh"
 #include "fa_fwd_sm100_persistent2.cuh"
 #include "fa_fwd_sm100_persist.cuh"
+#include "fa_fwd_sm100_d64.cuh"
 #include "fa_splitkv_combine.cuh"
 
 #include <cuda_runtime.h>
@@ -66,11 +67,11 @@ void init_dbg() {
 // (B?,H?,S,D)-strided 16-bit tensor -> 4-D tiled map with dims (D, S, H, B); the kernel addresses it as
 // (x = head-dim offset, y = sequence row, z = head, w = batch).  Box = 64 x 128 elements, SWIZZLE_128B.
 int make_tmap(CUtensorMap* m, const void* base, int dtype, int D, int S, int B, int H, long long sb,
-              long long sh, long long ss, int box_rows = 128) {
+              long long sh, long long ss, int box_rows = 128, int box_cols = 64) {
   auto encode = get_encode_fn();
   if (!encode) return TFA_EDRIVER;
   const CUtensorMapDataType dt = (dtype == TFA_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_rows), 1, 1};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const cuuint64_t dims[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(H),
                               static_cast<cuuint64_t>(B)};
@@ -82,7 +83,7 @@ int make_tmap(CUtensorMap* m, const void* base, int dtype, int D, int S, int B, 
   for (int i = 0; i < 3; ++i)
     if ((strides[i] % 16) || strides[i] >= (1ull << 40)) return TFA_EINVAL_STRIDE;
   CUresult r = encode(m, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : TFA_EDRIVER;
 }
@@ -96,27 +97,30 @@ int current_device() {
   return dev;
 }
 
-// ---- work counters of the persistent kernel: a small pool per device, one int per in-flight launch.  A slot is
-//      zeroed by a stream-ordered memset right before its launch and re-used only kNumSchedCounters launches later;
-//      the event recorded after each launch is waited for (host side) before the slot is handed out again, so two
-//      in-flight launches never share a counter. ----
+// ---- work counters of the persistent kernel: a small pool per device, one {next item, CTAs finished} pair per
+//      in-flight launch.  A pair is zero whenever no launch owns it: the pool is zeroed once at creation and the LAST CTA
+//      of a launch to run out of work resets its pair (fa_fwd_sm100_persist.cuh), so no memset sits in front of every
+//      launch.  A slot is re-used kNumSchedCounters launches later; the event recorded behind each launch is waited for
+//      (host side, normally long complete) before the slot is handed out again, so two in-flight launches never share one.
+//      (The round-1 experimental variants still get a stream-ordered memset: they do not reset.) ----
 constexpr int kNumSchedCounters = 64;
 struct SchedPool {
-  int* base = nullptr;
+  int* base = nullptr;                 // kNumSchedCounters x {counter, done}
   unsigned next = 0;
   cudaEvent_t done[kNumSchedCounters] = {};
   bool used[kNumSchedCounters] = {};
   std::mutex mu;
 };
 SchedPool g_sched[kMaxDevices];
-int* acquire_sched_counter(cudaStream_t stream, cudaError_t* err, int* slot_out) {
+int* acquire_sched_counter(cudaStream_t stream, cudaError_t* err, int* slot_out, bool self_resetting) {
   const int dev = current_device();
   if (dev < 0) { *err = cudaErrorInvalidDevice; return nullptr; }
   SchedPool& sp = g_sched[dev];
   std::lock_guard<std::mutex> lk(sp.mu);
   if (!sp.base) {
     void* d = nullptr;
-    if ((*err = cudaMalloc(&d, kNumSchedCounters * sizeof(int))) != cudaSuccess) return nullptr;
+    if ((*err = cudaMalloc(&d, kNumSchedCounters * 2 * sizeof(int))) != cudaSuccess) return nullptr;
+    if ((*err = cudaMemset(d, 0, kNumSchedCounters * 2 * sizeof(int))) != cudaSuccess) { cudaFree(d); return nullptr; }
     sp.base = static_cast<int*>(d);
   }
   const int slot = static_cast<int>(sp.next++ % kNumSchedCounters);
@@ -126,9 +130,9 @@ int* acquire_sched_counter(cudaStream_t stream, cudaError_t* err, int* slot_out)
     if ((*err = cudaEventCreateWithFlags(&sp.done[slot], cudaEventDisableTiming)) != cudaSuccess) return nullptr;
     sp.used[slot] = true;
   }
-  *err = cudaMemsetAsync(sp.base + slot, 0, sizeof(int), stream);   // ordered before the kernel on the same stream
+  *err = self_resetting ? cudaSuccess : cudaMemsetAsync(sp.base + 2 * slot, 0, 2 * sizeof(int), stream);
   *slot_out = slot;
-  return sp.base + slot;
+  return sp.base + 2 * slot;
 }
 void release_sched_counter(int slot, cudaStream_t stream) {
   const int dev = current_device();
@@ -158,6 +162,7 @@ int kernel_variant() {
     if (std::strcmp(e, "colsplit") == 0) return 2;     // experimental, see fa_fwd_sm100_colsplit.cuh
     if (std::strcmp(e, "persistent2") == 0) return 3;  // experimental, see fa_fwd_sm100_persistent2.cuh
     if (std::strcmp(e, "persist") == 0) return 4;      // fa_fwd_sm100_persist.cuh
+    if (std::strcmp(e, "persist64") == 0) return 5;    // persist for D=128, fa_fwd_sm100_d64.cuh (two softmax warpgroups per Q tile) for D=64
     return 0;
   }();
   return v;
@@ -176,20 +181,30 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   cudaError_t cerr = cudaSuccess;
   const bool plain = p.nsplit == 1 && p.kv_group == 1 && p.Sk == p.S;   // the persistent variants are square/MHA only
   const int variant = kernel_variant();
-  if (variant == 4) {
+  if (variant == 4 || variant == 5) {
     int slot = 0;
-    p.sched_counter = acquire_sched_counter(stream, &cerr, &slot);
+    p.sched_counter = acquire_sched_counter(stream, &cerr, &slot, true);
     if (cerr != cudaSuccess) return static_cast<int>(cerr);
     const int sms = num_sms();
     if (sms <= 0) return TFA_EARCH;
     const int nblocks = static_cast<int>(nitems < sms ? nitems : sms);       // one CTA per SM
+    if constexpr (D == 64) {
+      if (variant == 5) {
+        auto kern64 = tfa::fa_fwd_sm100_d64_kernel<CAUSAL, IS_BF16, OUT_F32>;
+        if ((cerr = opt_in_smem(kern64, tfa::P64Cfg::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
+        kern64<<<nblocks, tfa::P64Cfg::THREADS, tfa::P64Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+        release_sched_counter(slot, stream);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return static_cast<int>(cudaGetLastError());
+      }
+    }
     auto kern = tfa::fa_fwd_sm100_persist_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
     if ((cerr = opt_in_smem(kern, tfa::PCfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
     kern<<<nblocks, tfa::PCfg<D>::THREADS, tfa::PCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
     release_sched_counter(slot, stream);
   } else if ((variant == 1 || variant == 3) && plain) {
     int slot = 0;
-    p.sched_counter = acquire_sched_counter(stream, &cerr, &slot);
+    p.sched_counter = acquire_sched_counter(stream, &cerr, &slot, false);
     if (cerr != cudaSuccess) return static_cast<int>(cerr);
     const int sms = num_sms();
     if (sms <= 0) return TFA_EARCH;
@@ -337,7 +352,7 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
   const bool plain = (a.Sq == a.Sk) && (a.Hq == a.Hkv);
   if (n_extra > 0) {
     // fused exchange: 16-bit output of the reference-shaped problem only
-    if (n_extra > 7 || extra_dst == nullptr || f32 || (kernel_variant() != 0 && kernel_variant() != 4) || !plain || a.num_splits > 1)
+    if (n_extra > 7 || extra_dst == nullptr || f32 || (kernel_variant() != 0 && kernel_variant() < 4) || !plain || a.num_splits > 1)
       return TFA_EINVAL_SHAPE;
     for (int i = 0; i < n_extra; ++i)
       if (extra_dst[i] == nullptr || (reinterpret_cast<uintptr_t>(extra_dst[i]) & 15u)) return TFA_EINVAL_PTR;
@@ -386,10 +401,12 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
   // output tensor maps of the persistent kernel's TMA-store epilogue (16-bit output only): [0] = out, [1..] = peers
   tfa::OutMaps to;
   std::memset(&to, 0, sizeof(to));
-  if (kernel_variant() == 4 && !f32 && nsplit == 1) {
-    if ((rc = make_tmap(&to.m[0], a.out, a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss, 32))) return rc;
+  if (kernel_variant() >= 4 && !f32 && nsplit == 1) {
+    // store box: 32 rows x 64 columns (SWIZZLE_128B); the D=64 two-warpgroup kernel stores 32 x 32 (SWIZZLE_64B)
+    const int bc = (kernel_variant() == 5 && a.D == 64) ? 32 : 64;
+    if ((rc = make_tmap(&to.m[0], a.out, a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss, 32, bc))) return rc;
     for (int i = 0; i < n_extra; ++i)
-      if ((rc = make_tmap(&to.m[1 + i], extra_dst[i], a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss, 32))) return rc;
+      if ((rc = make_tmap(&to.m[1 + i], extra_dst[i], a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss, 32, bc))) return rc;
   }
 
   const long long rows = static_cast<long long>(a.B) * a.Hq * a.Sq;
