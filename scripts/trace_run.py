@@ -15,7 +15,8 @@ import tfa_ctypes  # noqa: E402
 ROLE = {0: "softmax0", 1: "softmax1", 2: "mma", 3: "loader"}
 EV_SM = {1: "start", 2: "S_ready", 3: "ld_done", 4: "max/rescale_done", 5: "exp/pack/st_issued", 6: "P_arrived", 7: "O_ready", 8: "epi_done"}
 EV_MMA = {1: "start", 2: "K0_ready", 3: "Q_ready", 4: "S(0)_issued", 5: "V_ready", 6: "P0_ready", 7: "P1_ready",
-          8: "PV0_issued", 9: "PV1_issued", 10: "K_ready", 12: "S0_next_issued", 13: "S1_next_issued"}
+          8: "PV0_issued", 9: "PV1_issued", 10: "K_ready", 12: "S0_next_issued", 13: "S1_next_issued",
+          14: "S0_HOISTED(next item)", 15: "S1_HOISTED(next item)"}
 EV_LD = {1: "start", 2: "slot_free"}
 
 

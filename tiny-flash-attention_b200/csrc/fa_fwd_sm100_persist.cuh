@@ -66,8 +66,19 @@ struct PItem {
   int nmax;
 };
 
+// Causal items are lopsided: the lower 128 rows see one KV tile more than the upper ones, and an item lasts as long as
+// its LONG tile's serial chain.  The tile that finishes first hoists its next first S and pre-computes that softmax
+// while the other tile finishes -- a head start of most of a step.  Alternating which tile RESOURCE (t = 0 / 1: Q
+// buffer, S/O columns, barriers, warpgroup) gets the long row block from one item of the CTA to the next hands that head
+// start to the long tile every time (`swap` = odd CTA-local item number).  -DTFA_ALTERNATE=0 disables (A/B).
+#ifndef TFA_HOIST
+#define TFA_HOIST 1          // 0: never issue the next item's first S early (A/B)
+#endif
+#ifndef TFA_ALTERNATE
+#define TFA_ALTERNATE 0
+#endif
 template <bool CAUSAL>
-__device__ __forceinline__ PItem decode_pitem(int item, const FwdParams& p) {
+__device__ __forceinline__ PItem decode_pitem(int item, const FwdParams& p, bool swap = false) {
   PItem w;
   int pr;
   decode_work(item, p.npairs, p.nsplit, p.head_chunk, p.BH, w.bh, w.split, pr);
@@ -84,6 +95,10 @@ __device__ __forceinline__ PItem decode_pitem(int item, const FwdParams& p) {
     w.nblk[t] = max(0, min(nfull - w.jb, p.split_tiles));
   }
   w.nmax = max(w.nblk[0], w.nblk[1]);
+  if (TFA_ALTERNATE && CAUSAL && swap) {
+    int x = w.row0[0]; w.row0[0] = w.row0[1]; w.row0[1] = x;
+    x = w.nblk[0]; w.nblk[0] = w.nblk[1]; w.nblk[1] = x;
+  }
   return w;
 }
 
@@ -106,6 +121,11 @@ __device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int x, 
 #ifndef TFA_Q_PREFETCH
 #define TFA_Q_PREFETCH 1
 #endif
+// 4-byte store through the async proxy that also completes 4 bytes of `bar`'s pending transaction count
+__device__ __forceinline__ void st_async_b32(uint32_t smem_addr, uint32_t v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(smem_addr), "r"(v), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -202,11 +222,15 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           if (decode_pitem<CAUSAL>(i, p).nmax > 0) return i;
         }
       };
+      // the item number travels WITH its signal: st.async writes the ring slot through the async proxy and completes
+      // the slot's mbarrier transaction count (same pattern as a TMA load feeding generic-proxy readers)
       auto publish = [&](int k, int item) {
         mbar_wait(bar(C::SCHED_EMPTY, k & 1), ((k >> 1) & 1) ^ 1, p.dbg, SITE_P_SCHED_EMPTY);
-        sched_ring[k & 1] = item;
-        mbar_arrive(bar(C::SCHED_FULL, k & 1));     // release: the store above is visible to the waiters
+        mbar_arrive_expect_tx(bar(C::SCHED_FULL, k & 1), 4);
+        st_async_b32(smem_u32(const_cast<int*>(&sched_ring[k & 1])), static_cast<uint32_t>(item), bar(C::SCHED_FULL, k & 1));
       };
+      TFA_TRACE_DECL(3)
+      TFA_TRACE_EV(1);
       uint32_t ent = 0;                        // running K/V ring entry (never reset between items)
       uint32_t qpar = 0;                       // bit t: parity of the next Q_EMPTY wait of tile t
       int k = 0;
@@ -215,7 +239,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       while (cur < total) {
         const int nxt = fetch();
         publish(k + 1, nxt);                   // consumers always know one item ahead
-        const PItem w = decode_pitem<CAUSAL>(cur, p);
+        const PItem w = decode_pitem<CAUSAL>(cur, p, k & 1);
 #if TFA_Q_PREFETCH
         if (nxt < total) {
           const PItem wn = decode_pitem<CAUSAL>(nxt, p);
@@ -241,6 +265,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           const uint32_t slot = ent & (NSTAGE - 1);
           const uint32_t par = (ent >> C::NSTAGE_LOG2) & 1u;
           mbar_wait(bar(C::KV_EMPTY, slot), par ^ 1u, p.dbg, SITE_LOAD_EMPTY);
+          TFA_TRACE_EV(2);
           mbar_arrive_expect_tx(bar(C::KV_FULL, slot), TILE);
           const CUtensorMap* tm = (kv == 0) ? &tmK : &tmV;
 #pragma unroll
@@ -313,6 +338,14 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       auto ent_slot = [&](uint32_t e) { return e & (NSTAGE - 1); };
       auto ent_par = [&](uint32_t e) { return (e >> C::NSTAGE_LOG2) & 1u; };
 
+      TFA_TRACE_DECL(2)
+#ifdef TFA_TRACE
+      const bool trace_on_mma = trace_on && (lane == 0);
+#define TFA_PTRACE_MMA(id) do { if (trace_on_mma) { TFA_TRACE_EV(id); } } while (0)
+#else
+#define TFA_PTRACE_MMA(id) do { } while (0)
+#endif
+      TFA_PTRACE_MMA(1);
       uint32_t ent_base = 0;       // ring entry of K_0 of the current item
       // per-tile 1-bit state in one register:  bit t: q_full parity | bit 2+t: P barriers' parity |
       //                                        bit 4+t: S_t(0) of the CURRENT item was already issued (hoisted)
@@ -322,7 +355,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       while (cur < total) {
         int n0, n1, nn0 = 0, nn1 = 0;
         {
-          const PItem x = decode_pitem<CAUSAL>(cur, p);
+          const PItem x = decode_pitem<CAUSAL>(cur, p, k & 1);
           n0 = x.nblk[0];
           n1 = x.nblk[1];
         }
@@ -330,7 +363,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         const int nxt = sched_get(k + 1);
         const bool has_nxt = nxt < total;
         if (has_nxt) {
-          const PItem x = decode_pitem<CAUSAL>(nxt, p);
+          const PItem x = decode_pitem<CAUSAL>(nxt, p, (k + 1) & 1);
           nn0 = x.nblk[0];
           nn1 = x.nblk[1];
         }
@@ -357,6 +390,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             const bool other_done = (no == 0) || ((st >> (4 + (t ^ 1))) & 1u) || (t == 1);
             first_S(t, nt, other_done, ent_base, SITE_P_FIRST_Q, SITE_P_FIRST_K);
             st |= (1u << (4 + t));
+            TFA_PTRACE_MMA(4);
           }
         }
         st &= ~(3u << 4);                      // the flags now describe the NEXT item: nothing hoisted yet
@@ -381,6 +415,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             const bool has_next = (j + 1 < nt);
             const uint32_t ppar = (st >> (2 + t)) & 1u;
             mbar_wait(bar(C::P_HALF, t), ppar, p.dbg, SITE_MMA_PH);
+            TFA_PTRACE_MMA(6 + t);
             tc_fence_after();
             issue_PV(t, vslot, j > 0, 0, 4, false, false);
             if (t == 1 && j + 1 < nmax) {
@@ -393,22 +428,25 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             tc_fence_after();
             issue_PV(t, vslot, true, 4, 6, false, false);
             mbar_wait(bar(C::P_FULL, t), ppar, p.dbg, SITE_MMA_P);
+            TFA_PTRACE_MMA(8 + t);
             st ^= (1u << (2 + t));
             tc_fence_after();
             issue_PV(t, vslot, true, 6, 8, last_v_user, !has_next);
             if (has_next) {
               issue_S(t, kslot, last_k_user, j + 2 == nt);
+              TFA_PTRACE_MMA(12 + t);
             } else {
               // Tile t is done with this item.  If the next item's Q_t and K_0 have ALREADY landed, issue its first S now:
               // the tensor pipe runs it while this tile's warpgroup does its epilogue and the other tile finishes.
               // Never block here: the other tile's P may be waiting for this warp.
               const int nnt = (t == 0) ? nn0 : nn1;
               const int nno = (t == 0) ? nn1 : nn0;
-              if (has_nxt && nnt > 0 && mbar_try_wait(bar(C::Q_FULL, t), (st >> t) & 1u) &&
+              if (TFA_HOIST && has_nxt && nnt > 0 && mbar_try_wait(bar(C::Q_FULL, t), (st >> t) & 1u) &&
                   mbar_try_wait(bar(C::KV_FULL, ent_slot(ent_next)), ent_par(ent_next))) {
                 const bool other_done = (nno == 0) || ((st >> (4 + (t ^ 1))) & 1u);
                 first_S(t, nnt, other_done, ent_next, SITE_P_FIRST_Q, SITE_P_FIRST_K);
                 st |= (1u << (4 + t));
+                TFA_PTRACE_MMA(14 + t);
               }
             }
           }
@@ -433,12 +471,20 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     const int S = p.S, Sk = p.Sk;
     const uint32_t stg = smem_u32(sStg) + warp * C::STG_WARP_BYTES;   // this warp's private staging (1024-aligned)
 
+    TFA_TRACE_DECL(t)
+#ifdef TFA_TRACE
+    const bool trace_on_sm = trace_on && (r == 0);
+#define TFA_PTRACE_SM(id) do { if (trace_on_sm) { TFA_TRACE_EV(id); } } while (0)
+#else
+#define TFA_PTRACE_SM(id) do { } while (0)
+#endif
+    TFA_PTRACE_SM(1);
     uint32_t scnt = 0;     // S tiles consumed  -> s_full / P barriers' parity
     uint32_t ocnt = 0;     // items finished    -> o_full parity
     for (int k = 0;; ++k) {
       const int item = sched_get(k);
       if (item >= total) break;
-      const PItem w = decode_pitem<CAUSAL>(item, p);
+      const PItem w = decode_pitem<CAUSAL>(item, p, k & 1);
       const int n = (t == 0) ? w.nblk[0] : w.nblk[1];
       if (n == 0) continue;
       const int trow0 = (t == 0) ? w.row0[0] : w.row0[1];
@@ -450,6 +496,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 
       for (int j = 0; j < n; ++j) {
         mbar_wait(bar(C::S_FULL, t), scnt & 1u, p.dbg, SITE_SM_S);
+        TFA_PTRACE_SM(2);
         tc_fence_after();
 
         // ---- S row -> registers: four back-to-back 32-column TMEM loads, ONE wait, mask, 4 independent max chains ----
@@ -477,6 +524,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           }
           mx = fmaxf(fmaxf(mxa, mxc), fmaxf(mxb, mxd));
         }
+        TFA_PTRACE_SM(3);
         if (j == 0) {
           m_ref = fmaxf(mx, -1.0e30f);                        // a fully masked row (split-KV) must not give -inf
         } else {
@@ -499,6 +547,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             }
           }
         }
+        TFA_PTRACE_SM(4);
         // ---- P = exp2(s*c - m_ref*c); l += rowsum(P) (fp32, before rounding); pack to 16 bit; three hand-offs ----
         constexpr int kEmuPairsPer8 = kEmuPairsPer8For<D>;
         const float2 c2 = make_float2(c, c);
@@ -527,15 +576,18 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(qt == 1 ? C::P_HALF : (qt == 2 ? C::P_3Q : C::P_FULL), t));
+            if (qt < 3) TFA_PTRACE_SM(5);
           }
         }
         acc0 = fadd2(acc0, acc1);
         l += acc0.x + acc0.y;
         ++scnt;
+        TFA_PTRACE_SM(6);
       }
 
       // ---------------------------- epilogue ----------------------------
       mbar_wait(bar(C::O_FULL, t), ocnt & 1u, p.dbg, SITE_EPI_O);
+      TFA_PTRACE_SM(7);
       ++ocnt;
       tc_fence_after();
       // a row none of whose keys lies in this item's KV range (split-KV partial above the row's causal limit): the
@@ -600,6 +652,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         }
       }
       tc_fence_before();
+      TFA_PTRACE_SM(8);
     }
     if (!OUT_F32 && lane == 0) bulk_wait_group0();          // all stores of this warp have completed before exit
   } else {
