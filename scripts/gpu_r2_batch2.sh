@@ -2,7 +2,8 @@
 # Round-2 GPU batch 2: full suites (default / persist / persist64), persist tuning variants, timelines.
 mkdir -p gpurun_out
 export TFA_NO_BUILD=1
-for v in default persist persist64; do
+timeout 300 python -m pytest tests/test_lazy_rescale.py tests/test_fused_exchange.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/b2_gpu_tests_default_new.log 2>&1; echo "new tests(default) rc=$?"; tail -3 gpurun_out/b2_gpu_tests_default_new.log | cut -c1-200
+for v in persist persist64; do
   [ "$v" = "default" ] && unset TFA_KERNEL || export TFA_KERNEL=$v
   timeout 900 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/b2_gpu_tests_$v.log 2>&1; echo "gpu_tests($v) rc=$?"; tail -6 gpurun_out/b2_gpu_tests_$v.log | cut -c1-200
 done

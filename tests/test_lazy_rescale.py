@@ -11,9 +11,10 @@ rounded to 16 bit (flash_attention_cutlass/csrc/flash_attention.cu:228-316,601; 
 
 Tolerances: LSE (= scale*m + ln l, no 16-bit rounding anywhere on its path) atol 2e-4 * max(1, |lse|) -- this is what
 pins the carried (m_ref, l) pair.  O: the kernel rounds P = 2^((s-m_ref)c) with a STALE m_ref, the reference rounds
-exp(scale(s-m)) with the true max; for near one-hot rows the dominant p is exactly 1.0 in the reference and an
-arbitrary value in [1, 2^8] here, so the two roundings differ by up to 2^-9 relative on the dominant term:
-|dO| <= 2^-9 * max|v| on top of the usual 1e-3 -- tested as atol 1e-3 + rtol 2^-8 (documented in DESIGN.md section 4)."""
+exp(scale(s-m)) with the true max.  Both round every p_i to 16 bit with a relative error <= 2^-9 (bf16) -- but they round
+DIFFERENT numbers (the two scalings differ by a factor that is not a power of two), so for peaked rows, where the errors
+do not average out, the two results differ by up to 2 * 2^-9 * sum_i p_i |v_i| / l.  That attention-weighted mean of |v|
+is computed by the oracle itself (same scores, values |v|); budget = 1e-3 + 2^-8 * attn(|v|) (fp16 P: 2^-11, same test)."""
 import numpy as np
 import pytest
 import torch
@@ -71,12 +72,12 @@ def make_case(pattern, B, Hq, Hkv, Sq, Sk, D, kind, seed=20):
     return q.to(dt).cuda(), k.to(dt).cuda(), v.to(dt).cuda(), scale
 
 
-def check(o32, lse, want32, want_lse):
+def check(o32, lse, want32, want_lse, want_abs):
     o = o32.float().cpu().numpy()
     l = lse.cpu().numpy()
     assert np.all(np.isfinite(o)), "non-finite output"
     d = np.abs(o - want32)
-    budget = ATOL + RTOL * np.abs(want32)
+    budget = ATOL + RTOL * want_abs                        # want_abs = attention-weighted mean of |v| (>= |O|)
     assert np.all(d <= budget), f"O: max excess {(d - budget).max():.3e} at {np.unravel_index((d - budget).argmax(), d.shape)}"
     fin = np.isfinite(want_lse)
     assert np.array_equal(np.isfinite(l), fin)
@@ -104,16 +105,17 @@ CASES = [
 def test_rescale_branch_matches_oracle(tfa, pattern, B, H, S, D, causal, kind):
     q, k, v, scale = make_case(pattern, B, H, H, S, S, D, kind)
     want32, want_lse = _oracle(q, k, v, causal, scale, kind)
+    want_abs, _ = _oracle(q, k, v.abs(), causal, scale, kind)
     o32, lse = tfa.fwd(q, k, v, causal, scale, out_fp32=True)
     torch.cuda.synchronize()
-    check(o32, lse, want32, want_lse)
+    check(o32, lse, want32, want_lse, want_abs)
     # the shipped 16-bit output is the rounding of the same arithmetic
     o16, lse2 = tfa.fwd(q, k, v, causal, scale)
     torch.cuda.synchronize()
     assert torch.equal(lse, lse2)
     ulp = 2.0 ** (np.floor(np.log2(np.maximum(np.abs(want32), 2.0 ** -14))) - (7 if kind == "bf16" else 10))
     d = np.abs(o16.float().cpu().numpy() - want32)
-    assert np.all(d <= ATOL + RTOL * np.abs(want32) + 0.505 * ulp)
+    assert np.all(d <= ATOL + RTOL * want_abs + 0.505 * ulp)
 
 
 @pytest.mark.parametrize("pattern,kind,D,causal", [("spread", "bf16", 128, True), ("staircase_up", "bf16", 64, False),
@@ -124,7 +126,8 @@ def test_rescale_branch_gqa_and_split_kv(tfa, pattern, kind, D, causal):
     B, Hq, Hkv, Sq, Sk = 1, 4, 2, 256, 1536
     q, k, v, scale = make_case(pattern, B, Hq, Hkv, Sq, Sk, D, kind)
     want32, want_lse = _oracle(q, k, v, causal, scale, kind)
+    want_abs, _ = _oracle(q, k, v.abs(), causal, scale, kind)
     for ns in (1, 3):
         o32, lse = tfa.attn_fwd(q, k, v, causal, scale, num_splits=ns, out_fp32=True)
         torch.cuda.synchronize()
-        check(o32, lse, want32, want_lse)
+        check(o32, lse, want32, want_lse, want_abs)

@@ -52,6 +52,7 @@ def _run(path, cwd, log_name):
     env = dict(os.environ, PYTHONPATH=PKG + os.pathsep + os.environ.get("PYTHONPATH", ""))
     p = subprocess.run([sys.executable, path], capture_output=True, text=True, timeout=600, env=env, cwd=cwd)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    log_name = log_name.replace(".log", "_" + os.environ.get("TFA_KERNEL", "default") + ".log")
     with open(os.path.join(ROOT, "gpurun_out", log_name), "w") as f:
         f.write(f"$ PYTHONPATH=tiny-flash-attention_b200 python {os.path.relpath(path, ROOT)}   (rc={p.returncode})\n")
         f.write(p.stdout + "\n--- stderr (tail) ---\n" + p.stderr[-3000:])

@@ -135,8 +135,8 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       };
       auto publish = [&](int k, int item) {
         mbar_wait(bar(C::SCHED_EMPTY, k & 1), ((k >> 1) & 1) ^ 1, p.dbg, SITE_P_SCHED_EMPTY);
-        mbar_arrive_expect_tx(bar(C::SCHED_FULL, k & 1), 4);
-        st_async_b32(smem_u32(const_cast<int*>(&sched_ring[k & 1])), static_cast<uint32_t>(item), bar(C::SCHED_FULL, k & 1));
+        sched_ring[k & 1] = item;
+        mbar_arrive(bar(C::SCHED_FULL, k & 1));     // release: the store above is visible to the waiters (acquire in try_wait)
       };
       uint32_t ent = 0, qpar = 0;
       int k = 0;

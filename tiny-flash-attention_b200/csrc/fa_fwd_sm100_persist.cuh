@@ -121,11 +121,6 @@ __device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int x, 
 #ifndef TFA_Q_PREFETCH
 #define TFA_Q_PREFETCH 1
 #endif
-// 4-byte store through the async proxy that also completes 4 bytes of `bar`'s pending transaction count
-__device__ __forceinline__ void st_async_b32(uint32_t smem_addr, uint32_t v, uint32_t bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(smem_addr), "r"(v), "r"(bar)
-               : "memory");
-}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -222,12 +217,13 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           if (decode_pitem<CAUSAL>(i, p).nmax > 0) return i;
         }
       };
-      // the item number travels WITH its signal: st.async writes the ring slot through the async proxy and completes
-      // the slot's mbarrier transaction count (same pattern as a TMA load feeding generic-proxy readers)
+      // (compute-sanitizer racecheck reports this store against the consumers' loads: it does not model mbarrier
+      // release/acquire for generic shared-memory accesses.  st.async, which would carry data and signal together, is
+      // an illegal instruction outside a cluster launch on sm_100a -- measured.)
       auto publish = [&](int k, int item) {
         mbar_wait(bar(C::SCHED_EMPTY, k & 1), ((k >> 1) & 1) ^ 1, p.dbg, SITE_P_SCHED_EMPTY);
-        mbar_arrive_expect_tx(bar(C::SCHED_FULL, k & 1), 4);
-        st_async_b32(smem_u32(const_cast<int*>(&sched_ring[k & 1])), static_cast<uint32_t>(item), bar(C::SCHED_FULL, k & 1));
+        sched_ring[k & 1] = item;
+        mbar_arrive(bar(C::SCHED_FULL, k & 1));     // release: the store above is visible to the waiters (acquire in try_wait)
       };
       TFA_TRACE_DECL(3)
       TFA_TRACE_EV(1);
