@@ -200,7 +200,7 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       auto issue_S = [&](int t, uint32_t kslot, bool release_kv, bool release_q) {
         const uint32_t q_lo = opaque(q_lo0) + t * SLOT_LO;
         const uint32_t k_lo = opaque(k_lo_base) + kslot * SLOT_LO;
-        const uint32_t d_tmem = opaque(tmem_base) + (t == 0 ? C::TM_S0 : C::TM_S1);
+        const uint32_t d_tmem = opaque(tmem_base) + t * (C::TM_S1 - C::TM_S0);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) umma_ss_lo(d_tmem, q_lo + k * 2, k_lo + k * 2, idescS, k > 0 ? 1u : 0u);
@@ -215,7 +215,7 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const uint32_t v_lo = opaque(v_lo_base) + vslot * SLOT_LO + h * (64 * 128 >> 4);   // 64 key rows = 8192 B
         const uint32_t tb = opaque(tmem_base);
         const uint32_t d_tmem = tb + C::TM_O + (2 * t + h) * 64;
-        const uint32_t p_tmem = tb + (t == 0 ? C::TM_S0 : C::TM_S1) + h * 64;
+        const uint32_t p_tmem = tb + t * (C::TM_S1 - C::TM_S0) + h * 64;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -256,7 +256,7 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           tc_fence_after();
           issue_S(t, ent_slot(e0), other_done, x_nt == 1);
         };
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < 2; ++t) {
           const int nt = (t == 0) ? n0 : n1;
           const int no = (t == 0) ? n1 : n0;
@@ -274,7 +274,7 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           // the 8-deep ring is far ahead: these waits are satisfied except right behind an item boundary
           mbar_wait(bar(C::KV_FULL, vslot), ent_par(ev), p.dbg, SITE_MMA_V);
           if (j + 1 < nmax) mbar_wait(bar(C::KV_FULL, kslot), ent_par(ek), p.dbg, SITE_MMA_K);
-#pragma unroll
+#pragma unroll 1
           for (int t = 0; t < 2; ++t) {
             const int nt = (t == 0) ? n0 : n1;
             const int no = (t == 0) ? n1 : n0;
@@ -296,18 +296,25 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             st ^= (1u << (2 + t));
             tc_fence_after();
             issue_PV(t, 1, vslot, true, 2, 4, last_v_user, !has_next);
-            if (has_next) {
-              issue_S(t, kslot, last_k_user, j + 2 == nt);
-            } else {
+            // ONE S site (instruction-cache footprint, see fa_fwd_sm100_persist.cuh): next KV tile, or the hoisted first
+            // S of the next item when its Q_t and K_0 have already landed
+            bool do_S = has_next, rel_kv = last_k_user, rel_q = (j + 2 == nt);
+            uint32_t s_slot = kslot;
+            if (!has_next) {
               const int nnt = (t == 0) ? nn0 : nn1;
               const int nno = (t == 0) ? nn1 : nn0;
-              if (has_nxt && nnt > 0 && mbar_try_wait(bar(C::Q_FULL, t), (st >> t) & 1u) &&
+              if (TFA_HOIST && has_nxt && nnt > 0 && mbar_try_wait(bar(C::Q_FULL, t), (st >> t) & 1u) &&
                   mbar_try_wait(bar(C::KV_FULL, ent_slot(ent_next)), ent_par(ent_next))) {
-                const bool other_done = (nno == 0) || ((st >> (4 + (t ^ 1))) & 1u);
-                first_S(t, nnt, other_done, ent_next);
+                st ^= (1u << t);
+                rel_kv = (nno == 0) || ((st >> (4 + (t ^ 1))) & 1u);
+                rel_q = (nnt == 1);
+                s_slot = ent_slot(ent_next);
                 st |= (1u << (4 + t));
+                do_S = true;
+                tc_fence_after();
               }
             }
+            if (do_S) issue_S(t, s_slot, rel_kv, rel_q);
           }
         }
         ent_base = ent_next;

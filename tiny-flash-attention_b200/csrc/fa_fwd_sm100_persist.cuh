@@ -125,6 +125,48 @@ __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bul
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- UMMA issue helpers.  The issuer warp runs its loop body once per ~2000 cycles while eight softmax warps stream
+// ~16 KB of unrolled math through the same instruction caches: an issuer unrolled over both tiles with the first-S code
+// inlined at four sites (~10 KB per loop trip, measured r02) misses the instruction cache on nearly every fetch and
+// stretches every "barrier satisfied -> MMA issued" gap (r02 timeline: issuer period 4080 cycles vs 3250).  So the
+// issuer below is ROLLED over the tile index and has ONE S site in its loop.  (Out-of-line functions would be smaller
+// still, but ptxas cannot allocate the 216-register softmax role once the kernel contains calls.)
+// Called with warp-uniform arguments by the whole (converged) issuer warp. ----
+template <int D, bool IS_BF16>
+__device__ __forceinline__ void pumma_issue_S(uint32_t d_tmem, uint32_t q_lo, uint32_t k_lo, uint32_t bar_s, uint32_t bar_kv,
+                                           uint32_t bar_q) {
+  if (elect_one()) {
+    const uint32_t idescS = umma_idesc_f16(IS_BF16 ? 1u : 0u, 128, 128, 0, 0);
+#pragma unroll
+    for (int k = 0; k < D / 16; ++k) {
+      const uint32_t off = (k / 4) * ((128 * 128) >> 4) + (k % 4) * 2;   // 16-byte units: next slab every 4 k-steps
+      umma_ss_lo(d_tmem, q_lo + off, k_lo + off, idescS, k > 0 ? 1u : 0u);
+    }
+    umma_commit(bar_s);
+    if (bar_kv != 0u) umma_commit(bar_kv);
+    if (bar_q != 0u) umma_commit(bar_q);
+  }
+  __syncwarp();
+}
+// O_t += P_t V for k-steps [k0, k1) (16 keys each); `acc` = accumulate onto O already at k0
+template <int D, bool IS_BF16>
+__device__ __forceinline__ void pumma_issue_PV(uint32_t d_tmem, uint32_t p_tmem, uint32_t v_lo, uint32_t acc, int k0, int k1,
+                                            uint32_t bar_kv, uint32_t bar_done) {
+  if (elect_one()) {
+    const uint32_t idescO = umma_idesc_f16(IS_BF16 ? 1u : 0u, 128, D, 0, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k >= k0 && k < k1) {
+        umma_ts_lo(d_tmem, p_tmem + k * 8, v_lo + k * 128, idescO, acc);
+        acc = 1u;
+      }
+    }
+    if (bar_kv != 0u) umma_commit(bar_kv);
+    if (bar_done != 0u) umma_commit(bar_done);
+  }
+  __syncwarp();
+}
+
 template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
 __global__ void __launch_bounds__(384, 1)
 fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -204,8 +246,20 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       // next non-empty work item (a split-KV item wholly above the causal diagonal has no tiles: never handed out)
       // p.sched_counter = {next item, CTAs that ran out of work}: both are 0 at launch, and the last CTA to draw the
       // terminator puts them back to 0 for the next launch that is handed this pair (no memset in front of each launch)
+#ifndef TFA_ONE_ITEM
+#define TFA_ONE_ITEM 0       // experiment: every CTA takes exactly one item (grid = number of items)
+#endif
+      int fetched = 0;
       auto fetch = [&]() -> int {
         for (;;) {
+          if (TFA_ONE_ITEM && fetched) {
+            if (atomicAdd(p.sched_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+              p.sched_counter[0] = 0;
+              p.sched_counter[1] = 0;
+            }
+            return total;
+          }
+          ++fetched;
           const int i = atomicAdd(p.sched_counter, 1);
           if (i >= total) {
             if (atomicAdd(p.sched_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
@@ -289,50 +343,23 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     setmaxnreg_dec<kRegsOther>();
     {
       const uint32_t tmem_base = read_tmem_base();
-      constexpr uint32_t FMT = IS_BF16 ? 1u : 0u;
-      const uint32_t idescS = umma_idesc_f16(FMT, 128, 128, 0, 0);  // A,B K-major
-      const uint32_t idescO = umma_idesc_f16(FMT, 128, D, 0, 1);    // B (=V) MN-major
-      auto opaque = [](uint32_t x) { uint32_t y; asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x)); return y; };
       const uint32_t q_lo0 = umma_desc_lo(sQ_addr, 16);
       const uint32_t k_lo_base = umma_desc_lo(sKV_addr, 16);
       const uint32_t v_lo_base = umma_desc_lo(sKV_addr, C::SLAB_BYTES);   // LBO = next 64-column slab
-
-      // S_t = Q_t K^T, commit -> s_full[t] (covers every earlier MMA incl. PV_t of the previous KV tile); optionally
-      // release the K slot (last user) and the Q buffer (last S of tile t in this item)
-      auto issue_S = [&](int t, uint32_t kslot, bool release_kv, bool release_q) {
-        const uint32_t q_lo = opaque(q_lo0) + t * SLOT_LO;
-        const uint32_t k_lo = opaque(k_lo_base) + kslot * SLOT_LO;
-        const uint32_t d_tmem = opaque(tmem_base) + (t == 0 ? C::TM_S0 : C::TM_S1);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint32_t off = (k / 4) * (C::SLAB_BYTES >> 4) + (k % 4) * 2;   // 16-byte units
-            umma_ss_lo(d_tmem, q_lo + off, k_lo + off, idescS, k > 0 ? 1u : 0u);
-          }
-          umma_commit(bar(C::S_FULL, t));
-          if (release_kv) umma_commit(bar(C::KV_EMPTY, kslot));
-          if (release_q) umma_commit(bar(C::Q_EMPTY, t));
-        }
-        __syncwarp();
-      };
-      // O_t += P_t V for k-steps [k0, k1): 16 kv rows per step = 2048 B (128 units)
-      auto issue_PV = [&](int t, uint32_t vslot, bool acc, int k0, int k1, bool release_kv, bool done) {
-        const uint32_t v_lo = opaque(v_lo_base) + vslot * SLOT_LO;
-        const uint32_t tb = opaque(tmem_base);
-        const uint32_t d_tmem = tb + (t == 0 ? C::TM_O0 : C::TM_O1);
-        const uint32_t p_tmem = tb + (t == 0 ? C::TM_S0 : C::TM_S1);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < C::BN / 16; ++k) {
-            if (k >= k0 && k < k1) umma_ts_lo(d_tmem, p_tmem + k * 8, v_lo + k * 128, idescO, (acc || k > 0) ? 1u : 0u);
-          }
-          if (release_kv) umma_commit(bar(C::KV_EMPTY, vslot));
-          if (done) umma_commit(bar(C::O_FULL, t));
-        }
-        __syncwarp();
-      };
       auto ent_slot = [&](uint32_t e) { return e & (NSTAGE - 1); };
       auto ent_par = [&](uint32_t e) { return (e >> C::NSTAGE_LOG2) & 1u; };
+      // S_t = Q_t K^T from ring slot `kslot`; commit -> s_full[t] (covers every earlier MMA incl. PV_t of the previous KV
+      // tile), optionally release the K slot (last user) and the Q buffer (last S of tile t in this item)
+      auto issue_S = [&](int t, uint32_t kslot, bool release_kv, bool release_q) {
+        pumma_issue_S<D, IS_BF16>(tmem_base + t * (C::TM_S1 - C::TM_S0), q_lo0 + t * SLOT_LO, k_lo_base + kslot * SLOT_LO,
+                                  bar(C::S_FULL, t), release_kv ? bar(C::KV_EMPTY, kslot) : 0u,
+                                  release_q ? bar(C::Q_EMPTY, t) : 0u);
+      };
+      auto issue_PV = [&](int t, uint32_t vslot, bool acc, int k0, int k1, bool release_kv, bool done) {
+        pumma_issue_PV<D, IS_BF16>(tmem_base + C::TM_O0 + t * (C::TM_O1 - C::TM_O0), tmem_base + t * (C::TM_S1 - C::TM_S0),
+                                   v_lo_base + vslot * SLOT_LO, acc ? 1u : 0u, k0, k1,
+                                   release_kv ? bar(C::KV_EMPTY, vslot) : 0u, done ? bar(C::O_FULL, t) : 0u);
+      };
 
       TFA_TRACE_DECL(2)
 #ifdef TFA_TRACE
@@ -349,7 +376,8 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       int k = 0;
       int cur = sched_get(0);
       while (cur < total) {
-        int n0, n1, nn0 = 0, nn1 = 0;
+        int nn[2] = {0, 0};
+        int n0, n1;
         {
           const PItem x = decode_pitem<CAUSAL>(cur, p, k & 1);
           n0 = x.nblk[0];
@@ -360,31 +388,30 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         const bool has_nxt = nxt < total;
         if (has_nxt) {
           const PItem x = decode_pitem<CAUSAL>(nxt, p, (k + 1) & 1);
-          nn0 = x.nblk[0];
-          nn1 = x.nblk[1];
+          nn[0] = x.nblk[0];
+          nn[1] = x.nblk[1];
         }
+        const int nn0 = nn[0], nn1 = nn[1];
         const uint32_t ent_next = ent_base + 2u * static_cast<uint32_t>(nmax);
 
-        // First S = Q_t K_0^T of an item whose K_0 sits at ring entry e0.  x_nt / x_no = that item's tile counts for
-        // tile t / the other tile.  K_0 is released by whichever tile issues its first S LAST: `other_done` says the
-        // other tile's first S of that item was already issued (or that tile is inactive).
-        auto first_S = [&](int t, int x_nt, bool other_done, uint32_t e0, uint32_t site_q, uint32_t site_k) {
-          mbar_wait(bar(C::Q_FULL, t), (st >> t) & 1u, p.dbg, site_q);
+        // First S = Q_t K_0^T of an item whose K_0 sits at ring entry e0.  K_0 is released by whichever tile issues its
+        // first S LAST: `other_done` says the other tile's first S of that item was already issued (or it is inactive).
+        auto first_S = [&](int t, int x_nt, bool other_done, uint32_t e0) {
+          mbar_wait(bar(C::Q_FULL, t), (st >> t) & 1u, p.dbg, SITE_P_FIRST_Q);
           st ^= (1u << t);
-          mbar_wait(bar(C::KV_FULL, ent_slot(e0)), ent_par(e0), p.dbg, site_k);
+          mbar_wait(bar(C::KV_FULL, ent_slot(e0)), ent_par(e0), p.dbg, SITE_P_FIRST_K);
           tc_fence_after();
           issue_S(t, ent_slot(e0), other_done, x_nt == 1);
         };
 
-        // prologue: whatever was not hoisted out of the previous item
-#pragma unroll
+        // prologue: whatever was not hoisted out of the previous item (rolled: one copy of the code)
+#pragma unroll 1
         for (int t = 0; t < 2; ++t) {
           const int nt = (t == 0) ? n0 : n1;
           const int no = (t == 0) ? n1 : n0;
           if (nt > 0 && !((st >> (4 + t)) & 1u)) {
-            // the other tile's first S is done if it was hoisted, if it is inactive, or (t == 1) if tile 0 just did it
             const bool other_done = (no == 0) || ((st >> (4 + (t ^ 1))) & 1u) || (t == 1);
-            first_S(t, nt, other_done, ent_base, SITE_P_FIRST_Q, SITE_P_FIRST_K);
+            first_S(t, nt, other_done, ent_base);
             st |= (1u << (4 + t));
             TFA_PTRACE_MMA(4);
           }
@@ -400,7 +427,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             if (j + 1 < nmax) mbar_wait(bar(C::KV_FULL, kslot), ent_par(ek), p.dbg, SITE_MMA_K);
           }
           kv_confirmed = false;
-#pragma unroll
+#pragma unroll 1
           for (int t = 0; t < 2; ++t) {
             const int nt = (t == 0) ? n0 : n1;
             const int no = (t == 0) ? n1 : n0;
@@ -428,22 +455,29 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             st ^= (1u << (2 + t));
             tc_fence_after();
             issue_PV(t, vslot, true, 6, 8, last_v_user, !has_next);
-            if (has_next) {
-              issue_S(t, kslot, last_k_user, j + 2 == nt);
-              TFA_PTRACE_MMA(12 + t);
-            } else {
-              // Tile t is done with this item.  If the next item's Q_t and K_0 have ALREADY landed, issue its first S now:
-              // the tensor pipe runs it while this tile's warpgroup does its epilogue and the other tile finishes.
-              // Never block here: the other tile's P may be waiting for this warp.
+            // ONE S site: the next KV tile of this item, or -- tile t is done with this item -- the first S of the NEXT
+            // item if its Q_t and K_0 have ALREADY landed (never block here: the other tile's P may be waiting for this
+            // warp): the tensor pipe runs it while this tile's warpgroup does its epilogue and the other tile finishes.
+            bool do_S = has_next, rel_kv = last_k_user, rel_q = (j + 2 == nt);
+            uint32_t s_slot = kslot;
+            if (!has_next) {
               const int nnt = (t == 0) ? nn0 : nn1;
               const int nno = (t == 0) ? nn1 : nn0;
               if (TFA_HOIST && has_nxt && nnt > 0 && mbar_try_wait(bar(C::Q_FULL, t), (st >> t) & 1u) &&
                   mbar_try_wait(bar(C::KV_FULL, ent_slot(ent_next)), ent_par(ent_next))) {
-                const bool other_done = (nno == 0) || ((st >> (4 + (t ^ 1))) & 1u);
-                first_S(t, nnt, other_done, ent_next, SITE_P_FIRST_Q, SITE_P_FIRST_K);
+                st ^= (1u << t);                                   // Q_FULL parity consumed
+                rel_kv = (nno == 0) || ((st >> (4 + (t ^ 1))) & 1u);   // K_0 is released by the LAST first-S of the item
+                rel_q = (nnt == 1);
+                s_slot = ent_slot(ent_next);
                 st |= (1u << (4 + t));
+                do_S = true;
+                tc_fence_after();
                 TFA_PTRACE_MMA(14 + t);
               }
+            }
+            if (do_S) {
+              issue_S(t, s_slot, rel_kv, rel_q);
+              TFA_PTRACE_MMA(12 + t);
             }
           }
         }
@@ -491,7 +525,17 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       float l = 0.f;       // running sum of exp2((s - m_ref) * c)
 
       for (int j = 0; j < n; ++j) {
+#if defined(TFA_SM_WAIT_HINT)
+        {
+          uint32_t ok = 0;
+          while (!ok) {
+            asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+                         : "=r"(ok) : "r"(bar(C::S_FULL, t)), "r"(scnt & 1u), "r"(1000000u) : "memory");
+          }
+        }
+#else
         mbar_wait(bar(C::S_FULL, t), scnt & 1u, p.dbg, SITE_SM_S);
+#endif
         TFA_PTRACE_SM(2);
         tc_fence_after();
 

@@ -9,9 +9,6 @@
 // caller's stream is honoured, nothing synchronises the device, nothing calls exit().
 #include "../../include/tfa_b200.h"
 #include "fa_fwd_sm100.cuh"
-#include "fa_fwd_sm100_persistent.cuh"
-#include "fa_fwd_sm100_colsplit.cuh"
-#include "fa_fwd_sm100_persistent2.cuh"
 #include "fa_fwd_sm100_persist.cuh"
 #include "fa_fwd_sm100_d64.cuh"
 #include "fa_splitkv_combine.cuh"
@@ -152,17 +149,17 @@ int num_sms() {
   return v;
 }
 
-// TFA_KERNEL=persistent selects the persistent variant (fa_fwd_sm100_persistent.cuh); default = one CTA per item.
-// 0 = default (one CTA per work item), 1 = persistent, 2 = column-split softmax (experimental)
+// Kernel selection.  TFA_KERNEL (read once): unset / "classic" = one CTA per work item (fa_fwd_sm100.cuh);
+// "persist" = persistent CTAs with cross-item overlap and the TMA-store epilogue (fa_fwd_sm100_persist.cuh);
+// "persist64" = persist for D=128 and the two-warpgroups-per-tile kernel (fa_fwd_sm100_d64.cuh) for D=64.
+// The round-1 experimental variants (column-split softmax, the first persistent kernel and its port) were measured on
+// B200 in round 2 -- 8-20 % slower than the classic kernel or faulting -- and removed (profiles/r02_variants_ab.txt).
 int kernel_variant() {
   static int v = [] {
     const char* e = std::getenv("TFA_KERNEL");
     if (e == nullptr) return 0;
-    if (std::strcmp(e, "persistent") == 0) return 1;
-    if (std::strcmp(e, "colsplit") == 0) return 2;     // experimental, see fa_fwd_sm100_colsplit.cuh
-    if (std::strcmp(e, "persistent2") == 0) return 3;  // experimental, see fa_fwd_sm100_persistent2.cuh
-    if (std::strcmp(e, "persist") == 0) return 4;      // fa_fwd_sm100_persist.cuh
-    if (std::strcmp(e, "persist64") == 0) return 5;    // persist for D=128, fa_fwd_sm100_d64.cuh (two softmax warpgroups per Q tile) for D=64
+    if (std::strcmp(e, "persist") == 0) return 4;
+    if (std::strcmp(e, "persist64") == 0) return 5;
     return 0;
   }();
   return v;
@@ -179,7 +176,6 @@ template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
 int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const tfa::OutMaps& to, FwdParams p,
                 long long nitems, cudaStream_t stream) {
   cudaError_t cerr = cudaSuccess;
-  const bool plain = p.nsplit == 1 && p.kv_group == 1 && p.Sk == p.S;   // the persistent variants are square/MHA only
   const int variant = kernel_variant();
   if (variant == 4 || variant == 5) {
     int slot = 0;
@@ -187,7 +183,10 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
     if (cerr != cudaSuccess) return static_cast<int>(cerr);
     const int sms = num_sms();
     if (sms <= 0) return TFA_EARCH;
-    const int nblocks = static_cast<int>(nitems < sms ? nitems : sms);       // one CTA per SM
+    int nblocks = static_cast<int>(nitems < sms ? nitems : sms);             // one CTA per SM
+#if defined(TFA_ONE_ITEM) && TFA_ONE_ITEM
+    nblocks = static_cast<int>(nitems);                                      // experiment: one item per CTA
+#endif
     if constexpr (D == 64) {
       if (variant == 5) {
         auto kern64 = tfa::fa_fwd_sm100_d64_kernel<CAUSAL, IS_BF16, OUT_F32>;
@@ -202,27 +201,6 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
     if ((cerr = opt_in_smem(kern, tfa::PCfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
     kern<<<nblocks, tfa::PCfg<D>::THREADS, tfa::PCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
     release_sched_counter(slot, stream);
-  } else if ((variant == 1 || variant == 3) && plain) {
-    int slot = 0;
-    p.sched_counter = acquire_sched_counter(stream, &cerr, &slot, false);
-    if (cerr != cudaSuccess) return static_cast<int>(cerr);
-    const int sms = num_sms();
-    if (sms <= 0) return TFA_EARCH;
-    const int nblocks = static_cast<int>(nitems < sms ? nitems : sms);       // one CTA per SM
-    if (variant == 1) {
-      auto kern = tfa::fa_fwd_sm100_persistent_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
-      if ((cerr = opt_in_smem(kern, tfa::PFwdCfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
-      kern<<<nblocks, tfa::PFwdCfg<D>::THREADS, tfa::PFwdCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
-    } else {
-      auto kern = tfa::fa_fwd_sm100_persistent2_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
-      if ((cerr = opt_in_smem(kern, tfa::P2Cfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
-      kern<<<nblocks, tfa::P2Cfg<D>::THREADS, tfa::P2Cfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
-    }
-    release_sched_counter(slot, stream);
-  } else if (variant == 2) {
-    auto kern = tfa::fa_fwd_sm100_colsplit_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
-    if ((cerr = opt_in_smem(kern, tfa::CsCfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
-    kern<<<static_cast<int>(nitems), tfa::CsCfg<D>::THREADS, tfa::CsCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   } else {
     auto kern = tfa::fa_fwd_sm100_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
     if ((cerr = opt_in_smem(kern, FwdCfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
