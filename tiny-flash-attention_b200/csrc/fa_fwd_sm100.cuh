@@ -104,7 +104,10 @@ struct FwdCfg {
   static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
   static constexpr int NSTAGE = (D == 128) ? 4 : 8; // K/V ring depth (tiles)
   static constexpr int NUM_BARS = 2 + 2 * NSTAGE + 2 + 2 + 2 + 2 + 2 + 2;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + 2 * TILE_BYTES + NSTAGE * TILE_BYTES + NUM_BARS * 8 + 16;
+#ifndef TFA_PAD_SMEM
+#define TFA_PAD_SMEM 0        // experiment: extra (unused) dynamic shared memory, to isolate the effect of the carve-out
+#endif
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + 2 * TILE_BYTES + NSTAGE * TILE_BYTES + NUM_BARS * 8 + 16 + TFA_PAD_SMEM;
   // TMEM columns (fp32): S0 | S1 | O0 | O1 ; P_t aliases the first 64 columns of S_t
   static constexpr int TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 256 + D;
   // D=64 leaves 128 TMEM columns unused.  -DTFA_D64_SEPARATE_P=1 (experiment, parity-tested) gives P_t its OWN 64

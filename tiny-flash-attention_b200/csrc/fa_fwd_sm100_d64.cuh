@@ -110,7 +110,12 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   };
   auto sched_get = [&](int k) -> int {
     mbar_wait(bar(C::SCHED_FULL, k & 1), (k >> 1) & 1, p.dbg, SITE_P_SCHED_FULL);
-    const int item = sched_ring[k & 1];
+    // REDUX makes the item number PROVABLY warp-uniform for the compiler.  Without it everything derived from a value
+    // loaded from shared memory (tile counts, loop bounds, ring slots, barrier parities, MMA descriptors) is treated as
+    // divergent: the issuer's operands go through vector registers + R2UR, every loop gets reconvergence scaffolding --
+    // measured on B200 (r02, profiles/r02_persist_bisect.txt): 25 % slower steady state, the whole deficit of the first
+    // persistent kernels, which round 1 had attributed to the instruction cache.
+    const int item = __reduce_max_sync(0xffffffffu, sched_ring[k & 1]);
     __syncwarp();
     if (lane == 0) mbar_arrive(bar(C::SCHED_EMPTY, k & 1));
     return item;

@@ -41,7 +41,13 @@ struct PCfg {
   static constexpr int NSTAGE = (D == 128) ? 4 : 8;                 // K/V ring depth (tiles), power of two
   static constexpr int NSTAGE_LOG2 = (D == 128) ? 2 : 3;
   static constexpr int STG_WARP_BYTES = 32 * 128;                   // epilogue staging: 32 rows x 128 B per softmax warp
-  static constexpr int STG_BYTES = 8 * STG_WARP_BYTES;
+#ifndef TFA_BISECT_NOSTG
+#define TFA_BISECT_NOSTG 0    // experiment (one-item mode only): no staging buffer, the epilogue stages in the dead Q tiles
+#endif
+#ifndef TFA_BISECT_NOSCHED
+#define TFA_BISECT_NOSCHED 0  // experiment (one-item mode only): no scheduler ring, item = blockIdx.x
+#endif
+  static constexpr int STG_BYTES = TFA_BISECT_NOSTG ? 0 : 8 * STG_WARP_BYTES;
   // barrier table (index of the first barrier of each kind)
   static constexpr uint32_t Q_FULL = 0, Q_EMPTY = 2, KV_FULL = 4, KV_EMPTY = KV_FULL + NSTAGE, S_FULL = KV_EMPTY + NSTAGE,
                             P_HALF = S_FULL + 2, P_3Q = P_HALF + 2, P_FULL = P_3Q + 2, O_FULL = P_FULL + 2,
@@ -232,8 +238,14 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 
   // consumer side of the scheduler ring: the k-th item handed to this CTA lives in slot k&1 (>= total: no more work)
   auto sched_get = [&](int k) -> int {
+    if (TFA_BISECT_NOSCHED) return k == 0 ? static_cast<int>(blockIdx.x) : total;
     mbar_wait(bar(C::SCHED_FULL, k & 1), (k >> 1) & 1, p.dbg, SITE_P_SCHED_FULL);
-    const int item = sched_ring[k & 1];
+    // REDUX makes the item number PROVABLY warp-uniform for the compiler.  Without it everything derived from a value
+    // loaded from shared memory (tile counts, loop bounds, ring slots, barrier parities, MMA descriptors) is treated as
+    // divergent: the issuer's operands go through vector registers + R2UR, every loop gets reconvergence scaffolding --
+    // measured on B200 (r02, profiles/r02_persist_bisect.txt): 25 % slower steady state, the whole deficit of the first
+    // persistent kernels, which round 1 had attributed to the instruction cache.
+    const int item = __reduce_max_sync(0xffffffffu, sched_ring[k & 1]);
     __syncwarp();
     if (lane == 0) mbar_arrive(bar(C::SCHED_EMPTY, k & 1));
     return item;
@@ -260,6 +272,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             return total;
           }
           ++fetched;
+          if (TFA_BISECT_NOSCHED) return static_cast<int>(blockIdx.x);
           const int i = atomicAdd(p.sched_counter, 1);
           if (i >= total) {
             if (atomicAdd(p.sched_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
@@ -275,6 +288,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       // release/acquire for generic shared-memory accesses.  st.async, which would carry data and signal together, is
       // an illegal instruction outside a cluster launch on sm_100a -- measured.)
       auto publish = [&](int k, int item) {
+        if (TFA_BISECT_NOSCHED) return;
         mbar_wait(bar(C::SCHED_EMPTY, k & 1), ((k >> 1) & 1) ^ 1, p.dbg, SITE_P_SCHED_EMPTY);
         sched_ring[k & 1] = item;
         mbar_arrive(bar(C::SCHED_FULL, k & 1));     // release: the store above is visible to the waiters (acquire in try_wait)
@@ -499,7 +513,8 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     const uint32_t tP = tS;
     const float c = p.scale_log2;
     const int S = p.S, Sk = p.Sk;
-    const uint32_t stg = smem_u32(sStg) + warp * C::STG_WARP_BYTES;   // this warp's private staging (1024-aligned)
+    const uint32_t stg = TFA_BISECT_NOSTG ? (sQ_addr + t * TILE + (warp & 3) * C::STG_WARP_BYTES)
+                                          : (smem_u32(sStg) + warp * C::STG_WARP_BYTES);   // this warp's private staging (1024-aligned)
 
     TFA_TRACE_DECL(t)
 #ifdef TFA_TRACE
