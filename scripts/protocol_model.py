@@ -250,32 +250,33 @@ class Sim:
                 kv_confirmed = False
                 for t in range(2):
                     nt, no = n[t], n[t ^ 1]
-                    if j >= nt:
-                        continue
+                    active = j < nt
                     last_v_user = (t == 1) or (j >= no)
                     last_k_user = (t == 1) or (j + 1 >= no)
                     has_next = j + 1 < nt
-                    ppar = p_par[t]
-                    yield lambda: self.p_half[t].done(ppar)
-                    issue_PV(cur, t, j, vslot, 1, False, False)
-                    if t == 1 and j + 1 < nmax:
-                        yield lambda: self.kv_full[slot_of(ev + 2)].done(par_of(ev + 2))
-                        if j + 2 < nmax:
-                            yield lambda: self.kv_full[slot_of(ek + 2)].done(par_of(ek + 2))
-                        kv_confirmed = True
-                    yield lambda: self.p_3q[t].done(ppar)
-                    issue_PV(cur, t, j, vslot, 2, False, False)
-                    yield lambda: self.p_full[t].done(ppar)
-                    p_par[t] ^= 1
-                    issue_PV(cur, t, j, vslot, 3, last_v_user, not has_next)
-                    if has_next:
+                    if active:
+                        ppar = p_par[t]
+                        yield lambda: self.p_half[t].done(ppar)
+                        issue_PV(cur, t, j, vslot, 1, False, False)
+                        if t == 1 and j + 1 < nmax:
+                            yield lambda: self.kv_full[slot_of(ev + 2)].done(par_of(ev + 2))
+                            if j + 2 < nmax:
+                                yield lambda: self.kv_full[slot_of(ek + 2)].done(par_of(ek + 2))
+                            kv_confirmed = True
+                        yield lambda: self.p_3q[t].done(ppar)
+                        issue_PV(cur, t, j, vslot, 2, False, False)
+                        yield lambda: self.p_full[t].done(ppar)
+                        p_par[t] ^= 1
+                        issue_PV(cur, t, j, vslot, 3, last_v_user, not has_next)
+                    if active and has_next:
                         issue_S(cur, t, j + 1, kslot, last_k_user, j + 2 == nt)
                     else:
                         nnt, nno = nn[t], nn[t ^ 1]
-                        if (self.hoist and has_nxt and nnt > 0 and self.q_full[t].done(qfull_par[t])
+                        if (self.hoist and has_nxt and nnt > 0 and not hoisted[t] and self.q_full[t].done(qfull_par[t])
                                 and self.kv_full[slot_of(ent_next)].done(par_of(ent_next))):
                             other_done = (nno == 0) or hoisted[t ^ 1]
-                            yield from first_S(nxt, t, nnt, other_done, ent_next)
+                            qfull_par[t] ^= 1
+                            issue_S(nxt, t, 0, slot_of(ent_next), other_done, nnt == 1)
                             hoisted[t] = True
             ent_base = ent_next
             cur = nxt

@@ -283,33 +283,41 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           for (int t = 0; t < 2; ++t) {
             const int nt = (t == 0) ? n0 : n1;
             const int no = (t == 0) ? n1 : n0;
-            if (j >= nt) continue;
+            const bool active = (j < nt);
             const bool last_v_user = (t == 1) || (j >= no);
             const bool last_k_user = (t == 1) || (j + 1 >= no);
             const bool has_next = (j + 1 < nt);
-            const uint32_t ppar = (st >> (2 + t)) & 1u;
-            mbar_wait(bar(C::P_HALF, 2 * t), ppar, p.dbg, SITE_MMA_PH);
-            tc_fence_after();
-            issue_PV(t, 0, vslot, j > 0, 0, 2, false, false);
-            mbar_wait(bar(C::P_HALF, 2 * t + 1), ppar, p.dbg, SITE_MMA_PH);
-            tc_fence_after();
-            issue_PV(t, 1, vslot, j > 0, 0, 2, false, false);
-            mbar_wait(bar(C::P_FULL, 2 * t), ppar, p.dbg, SITE_MMA_P);
-            tc_fence_after();
-            issue_PV(t, 0, vslot, true, 2, 4, false, false);
-            mbar_wait(bar(C::P_FULL, 2 * t + 1), ppar, p.dbg, SITE_MMA_P);
-            st ^= (1u << (2 + t));
-            tc_fence_after();
-            issue_PV(t, 1, vslot, true, 2, 4, last_v_user, !has_next);
+            if (active) {
+              const uint32_t ppar = (st >> (2 + t)) & 1u;
+              mbar_wait(bar(C::P_HALF, 2 * t), ppar, p.dbg, SITE_MMA_PH);
+              tc_fence_after();
+              issue_PV(t, 0, vslot, j > 0, 0, 2, false, false);
+              mbar_wait(bar(C::P_HALF, 2 * t + 1), ppar, p.dbg, SITE_MMA_PH);
+              tc_fence_after();
+              issue_PV(t, 1, vslot, j > 0, 0, 2, false, false);
+              mbar_wait(bar(C::P_FULL, 2 * t), ppar, p.dbg, SITE_MMA_P);
+              tc_fence_after();
+              issue_PV(t, 0, vslot, true, 2, 4, false, false);
+              mbar_wait(bar(C::P_FULL, 2 * t + 1), ppar, p.dbg, SITE_MMA_P);
+              st ^= (1u << (2 + t));
+              tc_fence_after();
+              issue_PV(t, 1, vslot, true, 2, 4, last_v_user, !has_next);
+            }
             // ONE S site (instruction-cache footprint, see fa_fwd_sm100_persist.cuh): next KV tile, or the hoisted first
-            // S of the next item when its Q_t and K_0 have already landed
-            bool do_S = has_next, rel_kv = last_k_user, rel_q = (j + 2 == nt);
+            // S of the next item as soon as its Q_t and K_0 have landed (non-blocking probe, retried while the other tile
+            // is still running)
+            bool do_S = active && has_next, rel_kv = last_k_user, rel_q = (j + 2 == nt);
             uint32_t s_slot = kslot;
-            if (!has_next) {
+            if (!do_S) {
               const int nnt = (t == 0) ? nn0 : nn1;
               const int nno = (t == 0) ? nn1 : nn0;
-              if (TFA_HOIST && has_nxt && nnt > 0 && mbar_try_wait(bar(C::Q_FULL, t), (st >> t) & 1u) &&
-                  mbar_try_wait(bar(C::KV_FULL, ent_slot(ent_next)), ent_par(ent_next))) {
+              bool landed = false;
+              if (TFA_HOIST && has_nxt && nnt > 0 && !((st >> (4 + t)) & 1u)) {
+                const bool q_ok = mbar_test_wait(bar(C::Q_FULL, t), (st >> t) & 1u);
+                const bool k_ok = mbar_test_wait(bar(C::KV_FULL, ent_slot(ent_next)), ent_par(ent_next));
+                landed = __all_sync(0xffffffffu, q_ok && k_ok);
+              }
+              if (landed) {
                 st ^= (1u << t);
                 rel_kv = (nno == 0) || ((st >> (4 + (t ^ 1))) & 1u);
                 rel_q = (nnt == 1);

@@ -273,7 +273,9 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           }
           ++fetched;
           if (TFA_BISECT_NOSCHED) return static_cast<int>(blockIdx.x);
-          const int i = atomicAdd(p.sched_counter, 1);
+          // CTA c starts with item c (no atomic, no ~1500-cycle round trip in front of the first load); the counter hands
+          // out the items from gridDim.x on
+          const int i = (fetched == 1) ? static_cast<int>(blockIdx.x) : atomicAdd(p.sched_counter, 1) + static_cast<int>(gridDim.x);
           if (i >= total) {
             if (atomicAdd(p.sched_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
               p.sched_counter[0] = 0;
@@ -301,20 +303,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       int cur = fetch();
       publish(0, cur);
       while (cur < total) {
-        const int nxt = fetch();
-        publish(k + 1, nxt);                   // consumers always know one item ahead
         const PItem w = decode_pitem<CAUSAL>(cur, p, k & 1);
-#if TFA_Q_PREFETCH
-        if (nxt < total) {
-          const PItem wn = decode_pitem<CAUSAL>(nxt, p);
-#pragma unroll
-          for (int t = 0; t < 2; ++t)
-            if (wn.nblk[t] > 0) {
-#pragma unroll
-              for (int sl = 0; sl < C::SLABS; ++sl) tma_prefetch_l2_4d(&tmQ, sl * 64, wn.row0[t], wn.hidx, wn.bidx);
-            }
-        }
-#endif
         auto load_q = [&](int t) {
           if (w.nblk[t] > 0) {
             mbar_wait(bar(C::Q_EMPTY, t), ((qpar >> t) & 1u) ^ 1u, p.dbg, SITE_P_QEMPTY);
@@ -338,11 +327,25 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
                         (w.jb + j) * C::BN, w.hkv, w.bidx);
           ++ent;
         };
-        // Q0, K0, V0 first (tile 0 can start), then Q1 (whose buffer frees last), then the rest of the ring
+        // Q0, K0, V0 first (tile 0 can start), then Q1 (whose buffer frees last) -- all BEFORE the next item number is
+        // drawn: the atomic's round trip must not sit in front of the loads the tensor pipe is waiting for
         load_q(0);
         load_kv(0, 0);
         load_kv(0, 1);
         load_q(1);
+        const int nxt = fetch();
+        publish(k + 1, nxt);                   // consumers learn the next item while they work on this one
+#if TFA_Q_PREFETCH
+        if (nxt < total) {
+          const PItem wn = decode_pitem<CAUSAL>(nxt, p);
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+            if (wn.nblk[t] > 0) {
+#pragma unroll
+              for (int sl = 0; sl < C::SLABS; ++sl) tma_prefetch_l2_4d(&tmQ, sl * 64, wn.row0[t], wn.hidx, wn.bidx);
+            }
+        }
+#endif
         for (int j = 1; j < w.nmax; ++j) {
           load_kv(j, 0);
           load_kv(j, 1);
@@ -398,14 +401,6 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           n1 = x.nblk[1];
         }
         const int nmax = max(n0, n1);
-        const int nxt = sched_get(k + 1);
-        const bool has_nxt = nxt < total;
-        if (has_nxt) {
-          const PItem x = decode_pitem<CAUSAL>(nxt, p, (k + 1) & 1);
-          nn[0] = x.nblk[0];
-          nn[1] = x.nblk[1];
-        }
-        const int nn0 = nn[0], nn1 = nn[1];
         const uint32_t ent_next = ent_base + 2u * static_cast<uint32_t>(nmax);
 
         // First S = Q_t K_0^T of an item whose K_0 sits at ring entry e0.  K_0 is released by whichever tile issues its
@@ -431,6 +426,15 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           }
         }
         st &= ~(3u << 4);                      // the flags now describe the NEXT item: nothing hoisted yet
+        // the next item is only needed for hoisting, i.e. from here on (the producer draws it after this item's first loads)
+        const int nxt = sched_get(k + 1);
+        const bool has_nxt = nxt < total;
+        if (has_nxt) {
+          const PItem x = decode_pitem<CAUSAL>(nxt, p, (k + 1) & 1);
+          nn[0] = x.nblk[0];
+          nn[1] = x.nblk[1];
+        }
+        const int nn0 = nn[0], nn1 = nn[1];
 
         bool kv_confirmed = false;             // V_j and K_{j+1} of the upcoming iteration already waited for
         for (int j = 0; j < nmax; ++j) {
@@ -445,40 +449,50 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           for (int t = 0; t < 2; ++t) {
             const int nt = (t == 0) ? n0 : n1;
             const int no = (t == 0) ? n1 : n0;
-            if (j >= nt) continue;
             // tile 0 is served first: it is the last user of V_j / K_{j+1} only when tile 1 does not use them
+            const bool active = (j < nt);
             const bool last_v_user = (t == 1) || (j >= no);
             const bool last_k_user = (t == 1) || (j + 1 >= no);
             const bool has_next = (j + 1 < nt);
-            const uint32_t ppar = (st >> (2 + t)) & 1u;
-            mbar_wait(bar(C::P_HALF, t), ppar, p.dbg, SITE_MMA_PH);
-            TFA_PTRACE_MMA(6 + t);
-            tc_fence_after();
-            issue_PV(t, vslot, j > 0, 0, 4, false, false);
-            if (t == 1 && j + 1 < nmax) {
-              // look-ahead: V_{j+1} and K_{j+2} were requested a full iteration ago; confirm them in the shadow of PV
-              mbar_wait(bar(C::KV_FULL, ent_slot(ev + 2u)), ent_par(ev + 2u), p.dbg, SITE_MMA_V);
-              if (j + 2 < nmax) mbar_wait(bar(C::KV_FULL, ent_slot(ek + 2u)), ent_par(ek + 2u), p.dbg, SITE_MMA_K);
-              kv_confirmed = true;
+            if (active) {
+              const uint32_t ppar = (st >> (2 + t)) & 1u;
+              mbar_wait(bar(C::P_HALF, t), ppar, p.dbg, SITE_MMA_PH);
+              TFA_PTRACE_MMA(6 + t);
+              tc_fence_after();
+              issue_PV(t, vslot, j > 0, 0, 4, false, false);
+              if (t == 1 && j + 1 < nmax) {
+                // look-ahead: V_{j+1} and K_{j+2} were requested a full iteration ago; confirm them in the shadow of PV
+                mbar_wait(bar(C::KV_FULL, ent_slot(ev + 2u)), ent_par(ev + 2u), p.dbg, SITE_MMA_V);
+                if (j + 2 < nmax) mbar_wait(bar(C::KV_FULL, ent_slot(ek + 2u)), ent_par(ek + 2u), p.dbg, SITE_MMA_K);
+                kv_confirmed = true;
+              }
+              mbar_wait(bar(C::P_3Q, t), ppar, p.dbg, SITE_MMA_P3);
+              tc_fence_after();
+              issue_PV(t, vslot, true, 4, 6, false, false);
+              mbar_wait(bar(C::P_FULL, t), ppar, p.dbg, SITE_MMA_P);
+              TFA_PTRACE_MMA(8 + t);
+              st ^= (1u << (2 + t));
+              tc_fence_after();
+              issue_PV(t, vslot, true, 6, 8, last_v_user, !has_next);
             }
-            mbar_wait(bar(C::P_3Q, t), ppar, p.dbg, SITE_MMA_P3);
-            tc_fence_after();
-            issue_PV(t, vslot, true, 4, 6, false, false);
-            mbar_wait(bar(C::P_FULL, t), ppar, p.dbg, SITE_MMA_P);
-            TFA_PTRACE_MMA(8 + t);
-            st ^= (1u << (2 + t));
-            tc_fence_after();
-            issue_PV(t, vslot, true, 6, 8, last_v_user, !has_next);
-            // ONE S site: the next KV tile of this item, or -- tile t is done with this item -- the first S of the NEXT
-            // item if its Q_t and K_0 have ALREADY landed (never block here: the other tile's P may be waiting for this
-            // warp): the tensor pipe runs it while this tile's warpgroup does its epilogue and the other tile finishes.
-            bool do_S = has_next, rel_kv = last_k_user, rel_q = (j + 2 == nt);
+            // ONE S site: the next KV tile of this item, or -- tile t is done with this item (just now, or in an earlier
+            // iteration while the other tile is still running) -- the first S of the NEXT item as soon as its Q_t and K_0
+            // have landed.  The probe never blocks (test_wait): the other tile's P may be waiting for this warp.  The
+            // tensor pipe runs the hoisted S while this tile's warpgroup does its epilogue and the other tile finishes.
+            bool do_S = active && has_next, rel_kv = last_k_user, rel_q = (j + 2 == nt);
             uint32_t s_slot = kslot;
-            if (!has_next) {
+            if (!do_S) {
               const int nnt = (t == 0) ? nn0 : nn1;
               const int nno = (t == 0) ? nn1 : nn0;
-              if (TFA_HOIST && has_nxt && nnt > 0 && mbar_try_wait(bar(C::Q_FULL, t), (st >> t) & 1u) &&
-                  mbar_try_wait(bar(C::KV_FULL, ent_slot(ent_next)), ent_par(ent_next))) {
+              // the probe result is voted: a per-thread predicate would make `st`, the slot and the release flags
+              // divergent in the compiler's eyes and drag the whole issue path onto vector registers (see sched_get)
+              bool landed = false;
+              if (TFA_HOIST && has_nxt && nnt > 0 && !((st >> (4 + t)) & 1u)) {
+                const bool q_ok = mbar_test_wait(bar(C::Q_FULL, t), (st >> t) & 1u);
+                const bool k_ok = mbar_test_wait(bar(C::KV_FULL, ent_slot(ent_next)), ent_par(ent_next));
+                landed = __all_sync(0xffffffffu, q_ok && k_ok);
+              }
+              if (landed) {
                 st ^= (1u << t);                                   // Q_FULL parity consumed
                 rel_kv = (nno == 0) || ((st >> (4 + (t ^ 1))) & 1u);   // K_0 is released by the LAST first-S of the item
                 rel_q = (nnt == 1);
