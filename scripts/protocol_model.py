@@ -113,8 +113,6 @@ class Sim:
         cur = self.fetch()
         yield from publish(0, cur)
         while cur < total:
-            nxt = self.fetch()
-            yield from publish(k + 1, nxt)
             n = self.items[cur]
             nmax = max(n)
 
@@ -147,6 +145,8 @@ class Sim:
             yield from load_kv(0, 'K')
             yield from load_kv(0, 'V')
             yield from load_q(1)
+            nxt = self.fetch()                 # the next item is drawn AFTER this item's first loads
+            yield from publish(k + 1, nxt)
             for j in range(1, nmax):
                 yield from load_kv(j, 'K')
                 yield from load_kv(j, 'V')
@@ -220,9 +220,6 @@ class Sim:
         while cur < total:
             n = self.items[cur]
             nmax = max(n)
-            nxt = yield from self.sched_get(k + 1)
-            has_nxt = nxt < total
-            nn = self.items[nxt] if has_nxt else (0, 0)
             ent_next = ent_base + 2 * nmax
 
             def first_S(item, t, x_nt, other_done, e0):
@@ -238,6 +235,9 @@ class Sim:
                     yield from first_S(cur, t, nt, other_done, ent_base)
                     hoisted[t] = True
             hoisted = [False, False]
+            nxt = yield from self.sched_get(k + 1)      # only needed for hoisting: after the prologue
+            has_nxt = nxt < total
+            nn = self.items[nxt] if has_nxt else (0, 0)
 
             kv_confirmed = False
             for j in range(nmax):
