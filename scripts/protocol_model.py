@@ -145,11 +145,11 @@ class Sim:
             yield from load_kv(0, 'K')
             yield from load_kv(0, 'V')
             yield from load_q(1)
-            nxt = self.fetch()                 # the next item is drawn AFTER this item's first loads
-            yield from publish(k + 1, nxt)
             for j in range(1, nmax):
                 yield from load_kv(j, 'K')
                 yield from load_kv(j, 'V')
+            nxt = self.fetch()                 # the next item is drawn as late as possible: after ALL loads of this item
+            yield from publish(k + 1, nxt)
             cur = nxt
             k += 1
 
@@ -235,9 +235,8 @@ class Sim:
                     yield from first_S(cur, t, nt, other_done, ent_base)
                     hoisted[t] = True
             hoisted = [False, False]
-            nxt = yield from self.sched_get(k + 1)      # only needed for hoisting: after the prologue
-            has_nxt = nxt < total
-            nn = self.items[nxt] if has_nxt else (0, 0)
+            nxt = None                                   # picked up lazily (non-blocking) at the hoist probes
+            nn = (0, 0)
 
             kv_confirmed = False
             for j in range(nmax):
@@ -271,6 +270,10 @@ class Sim:
                     if active and has_next:
                         issue_S(cur, t, j + 1, kslot, last_k_user, j + 2 == nt)
                     else:
+                        if self.hoist and not hoisted[t] and nxt is None and self.sched_full[(k + 1) & 1].done(((k + 1) >> 1) & 1):
+                            nxt = yield from self.sched_get(k + 1)
+                            nn = self.items[nxt] if nxt < total else (0, 0)
+                        has_nxt = nxt is not None and nxt < total
                         nnt, nno = nn[t], nn[t ^ 1]
                         if (self.hoist and has_nxt and nnt > 0 and not hoisted[t] and self.q_full[t].done(qfull_par[t])
                                 and self.kv_full[slot_of(ent_next)].done(par_of(ent_next))):
@@ -278,6 +281,8 @@ class Sim:
                             qfull_par[t] ^= 1
                             issue_S(nxt, t, 0, slot_of(ent_next), other_done, nnt == 1)
                             hoisted[t] = True
+            if nxt is None:
+                nxt = yield from self.sched_get(k + 1)
             ent_base = ent_next
             cur = nxt
             k += 1

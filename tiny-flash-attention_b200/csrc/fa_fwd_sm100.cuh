@@ -462,6 +462,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (n > 0) {
       const int r = threadIdx.x & 127;                       // row inside the Q tile == TMEM lane
       const int row_g = trow0 + r;                            // global query row
+      const int wq = __reduce_max_sync(0xffffffffu, warp & 3);   // warp index inside the warpgroup, PROVABLY uniform
       const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
       const uint32_t tmem_base = read_tmem_base();
       const uint32_t tS = tmem_base + lane_base + (t == 0 ? C::TM_S0 : C::TM_S1);
@@ -562,6 +563,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         constexpr int kEmuPairsPer8 = kEmuPairsPer8For<D>;
         const float2 c2 = make_float2(c, c);
         auto p_compute = [&](int qt, float2 nm2, float2& acc0, float2& acc1, uint32_t (&pk)[16]) {
+          if ((dead >> qt) & 1u) {                           // warp-uniform: every key of this quarter is masked
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            return;
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int pi = qt * 16 + i;
@@ -587,7 +593,6 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
         {
-          const float mx = row_max();
           TFA_TRACE_SM(3);
           if (j == 0) {
             m_ref = fmaxf(mx, -1.0e30f);                      // a fully masked row (split-KV) must not give -inf

@@ -125,9 +125,11 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     // ==================== scheduler + TMA producer (same protocol as fa_fwd_sm100_persist.cuh) ====================
     setmaxnreg_dec<C::REGS_OTHER>();
     if (lane == 0) {
+      bool first = true;                       // CTA c starts with item c: no atomic in front of the first loads
       auto fetch = [&]() -> int {
         for (;;) {
-          const int i = atomicAdd(p.sched_counter, 1);
+          const int i = first ? static_cast<int>(blockIdx.x) : atomicAdd(p.sched_counter, 1) + static_cast<int>(gridDim.x);
+          first = false;
           if (i >= total) {
             if (atomicAdd(p.sched_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
               p.sched_counter[0] = 0;
@@ -148,17 +150,7 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       int cur = fetch();
       publish(0, cur);
       while (cur < total) {
-        const int nxt = fetch();
-        publish(k + 1, nxt);
         const PItem w = decode_pitem<CAUSAL>(cur, p);
-#if TFA_Q_PREFETCH
-        if (nxt < total) {
-          const PItem wn = decode_pitem<CAUSAL>(nxt, p);
-#pragma unroll
-          for (int t = 0; t < 2; ++t)
-            if (wn.nblk[t] > 0) tma_prefetch_l2_4d(&tmQ, 0, wn.row0[t], wn.hidx, wn.bidx);
-        }
-#endif
         auto load_q = [&](int t) {
           if (w.nblk[t] > 0) {
             mbar_wait(bar(C::Q_EMPTY, t), ((qpar >> t) & 1u) ^ 1u, p.dbg, SITE_P_QEMPTY);
@@ -184,6 +176,16 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           load_kv(j, 0);
           load_kv(j, 1);
         }
+        const int nxt = fetch();               // drawn as late as the pipeline allows (see fa_fwd_sm100_persist.cuh)
+        publish(k + 1, nxt);
+#if TFA_Q_PREFETCH
+        if (nxt < total) {
+          const PItem wn = decode_pitem<CAUSAL>(nxt, p);
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+            if (wn.nblk[t] > 0) tma_prefetch_l2_4d(&tmQ, 0, wn.row0[t], wn.hidx, wn.bidx);
+        }
+#endif
         cur = nxt;
         ++k;
       }
@@ -246,13 +248,17 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           n1 = x.nblk[1];
         }
         const int nmax = max(n0, n1);
-        const int nxt = sched_get(k + 1);
-        const bool has_nxt = nxt < total;
-        if (has_nxt) {
-          const PItem x = decode_pitem<CAUSAL>(nxt, p);
-          nn0 = x.nblk[0];
-          nn1 = x.nblk[1];
-        }
+        int nxt = -1;                                        // picked up lazily, see fa_fwd_sm100_persist.cuh
+        auto poll_nxt = [&](bool block) {
+          if (nxt >= 0) return;
+          if (!block && !__all_sync(0xffffffffu, mbar_test_wait(bar(C::SCHED_FULL, (k + 1) & 1), ((k + 1) >> 1) & 1))) return;
+          nxt = sched_get(k + 1);
+          if (nxt < total) {
+            const PItem x = decode_pitem<CAUSAL>(nxt, p);
+            nn0 = x.nblk[0];
+            nn1 = x.nblk[1];
+          }
+        };
         const uint32_t ent_next = ent_base + 2u * static_cast<uint32_t>(nmax);
         auto first_S = [&](int t, int x_nt, bool other_done, uint32_t e0) {
           mbar_wait(bar(C::Q_FULL, t), (st >> t) & 1u, p.dbg, SITE_P_FIRST_Q);
@@ -309,9 +315,11 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             bool do_S = active && has_next, rel_kv = last_k_user, rel_q = (j + 2 == nt);
             uint32_t s_slot = kslot;
             if (!do_S) {
+              bool landed = false;
+              if (TFA_HOIST && !((st >> (4 + t)) & 1u)) poll_nxt(false);
+              const bool has_nxt = nxt >= 0 && nxt < total;
               const int nnt = (t == 0) ? nn0 : nn1;
               const int nno = (t == 0) ? nn1 : nn0;
-              bool landed = false;
               if (TFA_HOIST && has_nxt && nnt > 0 && !((st >> (4 + t)) & 1u)) {
                 const bool q_ok = mbar_test_wait(bar(C::Q_FULL, t), (st >> t) & 1u);
                 const bool k_ok = mbar_test_wait(bar(C::KV_FULL, ent_slot(ent_next)), ent_par(ent_next));
@@ -330,6 +338,7 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             if (do_S) issue_S(t, s_slot, rel_kv, rel_q);
           }
         }
+        poll_nxt(true);
         ent_base = ent_next;
         cur = nxt;
         ++k;
@@ -349,6 +358,7 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t tOt = tmem_base + lane_base + C::TM_O + (2 * t) * 64;                   // O_{t,A}; O_{t,B} = +64
     const float c = p.scale_log2;
     const int S = p.S, Sk = p.Sk;
+    const int wq = __reduce_max_sync(0xffffffffu, warp & 3);   // warp index inside the warpgroup, PROVABLY uniform
     const uint32_t stg = smem_u32(sStg) + warp * C::STG_WARP_BYTES;
     float2* xch = sXch + (t * 128 + r) * 2;
 
@@ -375,25 +385,49 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         int lim = Sk - col0;
         if (CAUSAL) lim = min(lim, row_g + p.causal_off - col0 + 1);
         float mx;
+        uint32_t dead = 0;                                   // bit c: 32-key chunk c of my half is masked for the whole warp
         {
           uint32_t sb[32];
           tmem_ld_x32(tS, sa);
           tmem_ld_x32(tS + 32, sb);
           tmem_wait_ld();
-          if (lim < 64) {
+          // masking by 32-key chunk, warp-uniformly (see fa_fwd_sm100_persist.cuh): untouched / dead / mixed
+          {
+            int lim_lo = Sk - col0, lim_hi = lim_lo;
+            if (CAUSAL) {
+              const int b0 = trow0 + wq * 32 + p.causal_off - col0 + 1;
+              lim_lo = min(lim_lo, b0);
+              lim_hi = min(lim_hi, b0 + 31);
+            }
+            if (lim_lo < 64) {
+              if (lim_hi <= 0) dead |= 1u;
+              else if (lim_lo < 32) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (i >= lim) sa[i] = 0xff800000u;
-              if (i + 32 >= lim) sb[i] = 0xff800000u;
+                for (int i = 0; i < 32; ++i)
+                  if (i >= lim) sa[i] = 0xff800000u;
+              }
+              if (lim_hi <= 32) dead |= 2u;
+              else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i + 32 >= lim) sb[i] = 0xff800000u;
+              }
             }
           }
           float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
+          if (!(dead & 1u)) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            mxa = fmax3(mxa, __uint_as_float(sa[i]), __uint_as_float(sa[i + 1]));
-            mxb = fmax3(mxb, __uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 3]));
-            mxc = fmax3(mxc, __uint_as_float(sb[i]), __uint_as_float(sb[i + 1]));
-            mxd = fmax3(mxd, __uint_as_float(sb[i + 2]), __uint_as_float(sb[i + 3]));
+            for (int i = 0; i < 32; i += 4) {
+              mxa = fmax3(mxa, __uint_as_float(sa[i]), __uint_as_float(sa[i + 1]));
+              mxb = fmax3(mxb, __uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 3]));
+            }
+          }
+          if (!(dead & 2u)) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              mxc = fmax3(mxc, __uint_as_float(sb[i]), __uint_as_float(sb[i + 1]));
+              mxd = fmax3(mxd, __uint_as_float(sb[i + 2]), __uint_as_float(sb[i + 3]));
+            }
           }
           mx = fmaxf(fmaxf(mxa, mxc), fmaxf(mxb, mxd));
         }
@@ -423,7 +457,8 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int qt = 0; qt < 2; ++qt) {
-          if (qt == 1) {
+          const bool dq = (dead >> qt) & 1u;                  // warp-uniform: every key of this quarter is masked
+          if (qt == 1 && !dq) {
             tmem_ld_x32(tS + 32, sa);                        // keys 32..63 again (their S columns are untouched so far)
             tmem_wait_ld();
             if (lim < 64) {
@@ -433,19 +468,24 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             }
           }
           uint32_t pk[16];
+          if (dq) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int pi = qt * 16 + i;
-            const float2 x = ffma2(make_float2(__uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1])), c2, nm2);
-            float2 e;
-            if (((pi * kEmuPairsPer8) & 7) < kEmuPairsPer8) {
-              e = ex2_poly2(x);
-            } else {
-              e.x = ex2_approx(x.x);
-              e.y = ex2_approx(x.y);
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int pi = qt * 16 + i;
+              const float2 x = ffma2(make_float2(__uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1])), c2, nm2);
+              float2 e;
+              if (((pi * kEmuPairsPer8) & 7) < kEmuPairsPer8) {
+                e = ex2_poly2(x);
+              } else {
+                e.x = ex2_approx(x.x);
+                e.y = ex2_approx(x.y);
+              }
+              if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
+              pk[i] = pack_16x2<IS_BF16>(e.x, e.y);
             }
-            if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
-            pk[i] = pack_16x2<IS_BF16>(e.x, e.y);
           }
           tmem_st_x16(tS + qt * 16, pk);
           tmem_wait_st();

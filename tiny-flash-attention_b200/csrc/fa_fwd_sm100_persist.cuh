@@ -333,8 +333,17 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         load_kv(0, 0);
         load_kv(0, 1);
         load_q(1);
+        for (int j = 1; j < w.nmax; ++j) {
+          load_kv(j, 0);
+          load_kv(j, 1);
+        }
+        // The next item is drawn as LATE as the pipeline allows: only now, with every load of this item issued (the ring
+        // keeps the producer ~2 KV tiles ahead of the tensor pipe, which is enough for the next Q/K_0 to land before the
+        // hoist point).  Drawing it an item ahead hands the last ~148 items of the queue to CTAs that are still busy
+        // instead of to idle ones: with the heaviest items of the last head chunk among them that cost ~10 % of the
+        // makespan on B4 H32 S4096 causal (r02, profiles/r02_persist_steps.md).
         const int nxt = fetch();
-        publish(k + 1, nxt);                   // consumers learn the next item while they work on this one
+        publish(k + 1, nxt);
 #if TFA_Q_PREFETCH
         if (nxt < total) {
           const PItem wn = decode_pitem<CAUSAL>(nxt, p);
@@ -346,10 +355,6 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             }
         }
 #endif
-        for (int j = 1; j < w.nmax; ++j) {
-          load_kv(j, 0);
-          load_kv(j, 1);
-        }
         cur = nxt;
         ++k;
       }
@@ -393,7 +398,6 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       int k = 0;
       int cur = sched_get(0);
       while (cur < total) {
-        int nn[2] = {0, 0};
         int n0, n1;
         {
           const PItem x = decode_pitem<CAUSAL>(cur, p, k & 1);
@@ -426,15 +430,19 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           }
         }
         st &= ~(3u << 4);                      // the flags now describe the NEXT item: nothing hoisted yet
-        // the next item is only needed for hoisting, i.e. from here on (the producer draws it after this item's first loads)
-        const int nxt = sched_get(k + 1);
-        const bool has_nxt = nxt < total;
-        if (has_nxt) {
-          const PItem x = decode_pitem<CAUSAL>(nxt, p, (k + 1) & 1);
-          nn[0] = x.nblk[0];
-          nn[1] = x.nblk[1];
-        }
-        const int nn0 = nn[0], nn1 = nn[1];
+        // The next item is only needed for hoisting and is published late (see the producer): it is picked up by a
+        // NON-blocking poll at the hoist probes and, at the latest, by a blocking read at the end of this item.
+        int nxt = -1, nn0 = 0, nn1 = 0;                      // -1 = not known yet
+        auto poll_nxt = [&](bool block) {
+          if (nxt >= 0) return;
+          if (!block && !__all_sync(0xffffffffu, mbar_test_wait(bar(C::SCHED_FULL, (k + 1) & 1), ((k + 1) >> 1) & 1))) return;
+          nxt = sched_get(k + 1);
+          if (nxt < total) {
+            const PItem x = decode_pitem<CAUSAL>(nxt, p, (k + 1) & 1);
+            nn0 = x.nblk[0];
+            nn1 = x.nblk[1];
+          }
+        };
 
         bool kv_confirmed = false;             // V_j and K_{j+1} of the upcoming iteration already waited for
         for (int j = 0; j < nmax; ++j) {
@@ -482,11 +490,13 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             bool do_S = active && has_next, rel_kv = last_k_user, rel_q = (j + 2 == nt);
             uint32_t s_slot = kslot;
             if (!do_S) {
-              const int nnt = (t == 0) ? nn0 : nn1;
-              const int nno = (t == 0) ? nn1 : nn0;
               // the probe result is voted: a per-thread predicate would make `st`, the slot and the release flags
               // divergent in the compiler's eyes and drag the whole issue path onto vector registers (see sched_get)
               bool landed = false;
+              if (TFA_HOIST && !((st >> (4 + t)) & 1u)) poll_nxt(false);
+              const bool has_nxt = nxt >= 0 && nxt < total;
+              const int nnt = (t == 0) ? nn0 : nn1;
+              const int nno = (t == 0) ? nn1 : nn0;
               if (TFA_HOIST && has_nxt && nnt > 0 && !((st >> (4 + t)) & 1u)) {
                 const bool q_ok = mbar_test_wait(bar(C::Q_FULL, t), (st >> t) & 1u);
                 const bool k_ok = mbar_test_wait(bar(C::KV_FULL, ent_slot(ent_next)), ent_par(ent_next));
@@ -509,6 +519,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             }
           }
         }
+        poll_nxt(true);
         ent_base = ent_next;
         cur = nxt;
         ++k;
