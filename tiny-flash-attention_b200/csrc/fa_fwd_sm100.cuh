@@ -497,10 +497,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_wait_ld();
         // Masking, by 32-key chunk and warp-uniformly.  A thread's limit is lim = min(Sk - col0, b0 + lane): monotone in
         // the lane, so per chunk the whole warp is either untouched (lim_lo >= chunk end: nothing to do), dead (lim_hi <=
-        // chunk start: no max, no exponentials, P = 0) or mixed (per-element select; at most two chunks of a tile).  The
-        // old per-element pass over all 128 scores cost ~1260 cycles on every diagonal tile (r02 timeline) -- two tiles per
-        // causal work item.
-        uint32_t dead = 0;                                   // bit q4: chunk q4 is masked for every row of this warp
+        // chunk start: 32 moves) or mixed (per-element select; at most two chunks of a tile).  The old per-element pass
+        // over all 128 scores cost ~1260 cycles on every diagonal tile (r02 timeline) -- two tiles per causal work item.
         {
           int lim_lo = Sk - col0, lim_hi = lim_lo;
           if (CAUSAL) {
@@ -512,29 +510,29 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               if (lim_hi <= q4 * 32) {
-                dead |= 1u << q4;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sr[q4 * 32 + i] = 0xff800000u;   // dead chunk: -inf, no compares
               } else if (lim_lo < q4 * 32 + 32) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                  if (q4 * 32 + i >= lim) sr[q4 * 32 + i] = 0xff800000u;   // -inf
+                  if (q4 * 32 + i >= lim) sr[q4 * 32 + i] = 0xff800000u;       // mixed chunk: per-element select
               }
             }
           }
         }
         float mx;
         {
-          float mq[4];
+          // four INTERLEAVED max chains over all 128 scores (per-chunk chains behind per-chunk branches serialise: measured
+          // +210 cycles per tile, r02 batch 9)
+          float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {                   // one max chain per chunk: four independent chains
-            float m4 = -INFINITY;
-            if (!((dead >> q4) & 1u)) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 2)
-                m4 = fmax3(m4, __uint_as_float(sr[q4 * 32 + i]), __uint_as_float(sr[q4 * 32 + i + 1]));
-            }
-            mq[q4] = m4;
+          for (int i = 0; i < 128; i += 8) {
+            mxa = fmax3(mxa, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
+            mxb = fmax3(mxb, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
+            mxc = fmax3(mxc, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
+            mxd = fmax3(mxd, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
           }
-          mx = fmaxf(fmaxf(mq[0], mq[2]), fmaxf(mq[1], mq[3]));
+          mx = fmaxf(fmaxf(mxa, mxc), fmaxf(mxb, mxd));
         }
         // lazy rescale of l and O: only when the row max moved by more than 2^8 (warp-uniform branch, rare)
         auto rescale_if_needed = [&](float mx) -> bool {
@@ -563,11 +561,6 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         constexpr int kEmuPairsPer8 = kEmuPairsPer8For<D>;
         const float2 c2 = make_float2(c, c);
         auto p_compute = [&](int qt, float2 nm2, float2& acc0, float2& acc1, uint32_t (&pk)[16]) {
-          if ((dead >> qt) & 1u) {                           // warp-uniform: every key of this quarter is masked
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = 0u;
-            return;
-          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int pi = qt * 16 + i;

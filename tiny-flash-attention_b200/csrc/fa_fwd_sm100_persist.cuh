@@ -590,10 +590,8 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         tmem_wait_ld();
         // Masking, by 32-key chunk and warp-uniformly.  A thread's limit is lim = min(Sk - col0, b0 + lane): monotone in
         // the lane, so per chunk the whole warp is either untouched (lim_lo >= chunk end: nothing to do), dead (lim_hi <=
-        // chunk start: no max, no exponentials, P = 0) or mixed (per-element select; at most two chunks of a tile).  The
-        // old per-element pass over all 128 scores cost ~1260 cycles on every diagonal tile (r02 timeline) -- two tiles per
-        // causal work item.
-        uint32_t dead = 0;                                   // bit q4: chunk q4 is masked for every row of this warp
+        // chunk start: 32 moves) or mixed (per-element select; at most two chunks of a tile).  The old per-element pass
+        // over all 128 scores cost ~1260 cycles on every diagonal tile (r02 timeline) -- two tiles per causal work item.
         {
           int lim_lo = Sk - col0, lim_hi = lim_lo;
           if (CAUSAL) {
@@ -605,29 +603,29 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               if (lim_hi <= q4 * 32) {
-                dead |= 1u << q4;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sr[q4 * 32 + i] = 0xff800000u;   // dead chunk: -inf, no compares
               } else if (lim_lo < q4 * 32 + 32) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                  if (q4 * 32 + i >= lim) sr[q4 * 32 + i] = 0xff800000u;   // -inf
+                  if (q4 * 32 + i >= lim) sr[q4 * 32 + i] = 0xff800000u;       // mixed chunk: per-element select
               }
             }
           }
         }
         float mx;
         {
-          float mq[4];
+          // four INTERLEAVED max chains over all 128 scores (per-chunk chains behind per-chunk branches serialise: measured
+          // +210 cycles per tile, r02 batch 9)
+          float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {                   // one max chain per chunk: four independent chains
-            float m4 = -INFINITY;
-            if (!((dead >> q4) & 1u)) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 2)
-                m4 = fmax3(m4, __uint_as_float(sr[q4 * 32 + i]), __uint_as_float(sr[q4 * 32 + i + 1]));
-            }
-            mq[q4] = m4;
+          for (int i = 0; i < 128; i += 8) {
+            mxa = fmax3(mxa, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
+            mxb = fmax3(mxb, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
+            mxc = fmax3(mxc, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
+            mxd = fmax3(mxd, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
           }
-          mx = fmaxf(fmaxf(mq[0], mq[2]), fmaxf(mq[1], mq[3]));
+          mx = fmaxf(fmaxf(mxa, mxc), fmaxf(mxb, mxd));
         }
         TFA_PTRACE_SM(3);
         if (j == 0) {
@@ -661,24 +659,19 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 #pragma unroll
         for (int qt = 0; qt < 4; ++qt) {
           uint32_t pk[16];
-          if ((dead >> qt) & 1u) {                           // warp-uniform: every key of this quarter is masked
 #pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = 0u;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int pi = qt * 16 + i;
-              const float2 x = ffma2(make_float2(__uint_as_float(sr[2 * pi]), __uint_as_float(sr[2 * pi + 1])), c2, nm2);
-              float2 e;
-              if (((pi * kEmuPairsPer8) & 7) < kEmuPairsPer8) {
-                e = ex2_poly2(x);
-              } else {
-                e.x = ex2_approx(x.x);
-                e.y = ex2_approx(x.y);
-              }
-              if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
-              pk[i] = pack_16x2<IS_BF16>(e.x, e.y);
+          for (int i = 0; i < 16; ++i) {
+            const int pi = qt * 16 + i;
+            const float2 x = ffma2(make_float2(__uint_as_float(sr[2 * pi]), __uint_as_float(sr[2 * pi + 1])), c2, nm2);
+            float2 e;
+            if (((pi * kEmuPairsPer8) & 7) < kEmuPairsPer8) {
+              e = ex2_poly2(x);
+            } else {
+              e.x = ex2_approx(x.x);
+              e.y = ex2_approx(x.y);
             }
+            if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
+            pk[i] = pack_16x2<IS_BF16>(e.x, e.y);
           }
           tmem_st_x16(tP + qt * 16, pk);
           if (qt >= 1) {       // hand-offs after keys 0..63 (p_half), 64..95 (p_3q), 96..127 (p_full)
