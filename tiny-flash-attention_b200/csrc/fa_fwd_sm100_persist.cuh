@@ -538,7 +538,6 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     const uint32_t tP = tS;
     const float c = p.scale_log2;
     const int S = p.S, Sk = p.Sk;
-    const int wq = __reduce_max_sync(0xffffffffu, warp & 3);   // warp index inside the warpgroup, PROVABLY uniform
     const uint32_t stg = TFA_BISECT_NOSTG ? (sQ_addr + t * TILE + (warp & 3) * C::STG_WARP_BYTES)
                                           : (smem_u32(sStg) + warp * C::STG_WARP_BYTES);   // this warp's private staging (1024-aligned)
 
@@ -588,35 +587,16 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) tmem_ld_x32(tS + q4 * 32, &sr[q4 * 32]);
         tmem_wait_ld();
-        // Masking, by 32-key chunk and warp-uniformly.  A thread's limit is lim = min(Sk - col0, b0 + lane): monotone in
-        // the lane, so per chunk the whole warp is either untouched (lim_lo >= chunk end: nothing to do), dead (lim_hi <=
-        // chunk start: 32 moves) or mixed (per-element select; at most two chunks of a tile).  The old per-element pass
-        // over all 128 scores cost ~1260 cycles on every diagonal tile (r02 timeline) -- two tiles per causal work item.
-        {
-          int lim_lo = Sk - col0, lim_hi = lim_lo;
-          if (CAUSAL) {
-            const int b0 = trow0 + wq * 32 + p.causal_off - col0 + 1;
-            lim_lo = min(lim_lo, b0);
-            lim_hi = min(lim_hi, b0 + 31);
-          }
-          if (lim_lo < C::BN) {
+        // (Tried in r02 and measured slower on B200: chunk-wise warp-uniform masking -- per-chunk max chains behind branches
+        //  serialise (+210 cycles per tile), writing -inf into dead chunks under a branch makes ptxas handle the whole 128-
+        //  register row conditionally (+1600).  The per-element select below only runs on diagonal / ragged tiles.)
+        if (lim < C::BN) {
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              if (lim_hi <= q4 * 32) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) sr[q4 * 32 + i] = 0xff800000u;   // dead chunk: -inf, no compares
-              } else if (lim_lo < q4 * 32 + 32) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (q4 * 32 + i >= lim) sr[q4 * 32 + i] = 0xff800000u;       // mixed chunk: per-element select
-              }
-            }
-          }
+          for (int i = 0; i < 128; ++i)
+            if (i >= lim) sr[i] = 0xff800000u;                 // -inf
         }
         float mx;
         {
-          // four INTERLEAVED max chains over all 128 scores (per-chunk chains behind per-chunk branches serialise: measured
-          // +210 cycles per tile, r02 batch 9)
           float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 128; i += 8) {
