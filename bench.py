@@ -384,6 +384,7 @@ def run_ours(args):
     F_job = flops_effective(B, H, S, D)
     value = F_job / t_step / 1e12
 
+    kernel_main = kernel_name(tfa)
     # ---- roofline: the dominant (only) kernel, from the events recorded INSIDE the timed region ----
     k_times = [a_.elapsed_time(b_) * 1e-3 for a_, b_ in kernel_events]
     k_mean, k_min = sum(k_times) / len(k_times), min(k_times)
@@ -400,7 +401,7 @@ def run_ours(args):
         t_flops = F_launch / (peak * 1e12)
         t_link = nv_bytes / 770e9
         target = max(t_flops, t_link)
-        fused_roofline = {"kernel": "fa_fwd_sm100_kernel + peer stores (tfa_fwd_multi)", "nvlink_bytes_out_per_launch": nv_bytes,
+        fused_roofline = {"kernel": kernel_main + " + peer stores (tfa_fwd_multi)", "nvlink_bytes_out_per_launch": nv_bytes,
                           "nvlink_peak_GBps": 770.0, "t_tensor_ms": t_flops * 1e3, "t_nvlink_ms": t_link * 1e3,
                           "target_ms": target * 1e3, "achieved_ms": k_mean * 1e3, "frac": target / k_mean,
                           "bound": "nvlink" if t_link > t_flops else "tensor"}
@@ -498,7 +499,7 @@ def run_ours(args):
             ll = torch.empty(b_, h_, s_, dtype=torch.float32, device=dev)
             mean, med, mn = time_kernel(tfa, qq, kk, vv, c_, 1.0 / math.sqrt(d_), oo, ll, reps=20, warm=5, flush=flush)
             Fe, Fs = flops_effective(b_, h_, s_, d_), flops_std(b_, h_, s_, d_, c_)
-            configs[name] = {"ms": med * 1e3, "tflops": Fe / med / 1e12, "tflops_std": Fs / med / 1e12,
+            configs[name] = {"kernel": kernel_name(tfa).split(" ")[0], "ms": med * 1e3, "tflops": Fe / med / 1e12, "tflops_std": Fs / med / 1e12,
                              "roofline_frac": Fe / med / 1e12 / peak, "roofline_frac_std": Fs / med / 1e12 / peak,
                              "l2": "256 MB flush between reps"}
             del qq, kk, vv, oo, ll
@@ -608,7 +609,7 @@ def run_ours(args):
                      "frac": achieved / roof_peak,
                      "frac_of_burst_peak": achieved / peak, "frac_of_sustained_peak": achieved / peak_sus,
                      "peak_source": f"MEASURED_PEAKS.json ({peak_src}): " + roof_peak_name,
-                     "kernel": KERNEL_NAME, "kernel_ms_mean": k_mean * 1e3, "kernel_ms_min": k_min * 1e3,
+                     "kernel": kernel_main, "kernel_ms_mean": k_mean * 1e3, "kernel_ms_min": k_min * 1e3,
                      "timing": "CUDA events around each launch inside the timed region",
                      "flops_per_launch": F_launch, "launches_per_step_per_rank": launches_per_step,
                      "traffic": traffic, "traffic_source": traffic_src,
@@ -634,7 +635,16 @@ def q_bytes(B, H, S, D):
     return B * H * S * D * 2
 
 
-KERNEL_NAME = "fa_fwd_sm100_kernel<128,causal,bf16>"
+def kernel_name(tfa):
+    """Name of the kernel the library's AUTO choice (csrc/tfa_api.cu choose_kernel) used for the last launch."""
+    try:
+        v = int(tfa.lib().tfa_internal_last_variant())
+    except Exception:  # noqa: BLE001
+        v = 0
+    return {0: "fa_fwd_sm100_kernel<128,causal,bf16> (one CTA per work item)",
+            4: "fa_fwd_sm100_persist_kernel<128,causal,bf16> (persistent, TMA-store epilogue)",
+            5: "fa_fwd_sm100_d64_kernel"}.get(v, str(v))
+
 
 
 def profiled_traffic(heads_per_launch):

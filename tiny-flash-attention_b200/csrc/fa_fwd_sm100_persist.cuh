@@ -77,6 +77,10 @@ struct PItem {
 // while the other tile finishes -- a head start of most of a step.  Alternating which tile RESOURCE (t = 0 / 1: Q
 // buffer, S/O columns, barriers, warpgroup) gets the long row block from one item of the CTA to the next hands that head
 // start to the long tile every time (`swap` = odd CTA-local item number).  -DTFA_ALTERNATE=0 disables (A/B).
+#ifndef TFA_ISSUER_UNROLL_T
+#define TFA_ISSUER_UNROLL_T 1   // the issuer's main loop is unrolled over the two tiles: compile-time tile index on the issue
+                                // path; measured +3 % over the rolled loop once the item number was warp-uniform (r02)
+#endif
 #ifndef TFA_HOIST
 #define TFA_HOIST 1          // 0: never issue the next item's first S early (A/B)
 #endif
@@ -453,7 +457,11 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             if (j + 1 < nmax) mbar_wait(bar(C::KV_FULL, kslot), ent_par(ek), p.dbg, SITE_MMA_K);
           }
           kv_confirmed = false;
+#if TFA_ISSUER_UNROLL_T
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
           for (int t = 0; t < 2; ++t) {
             const int nt = (t == 0) ? n0 : n1;
             const int no = (t == 0) ? n1 : n0;

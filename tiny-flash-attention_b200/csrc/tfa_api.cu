@@ -28,6 +28,7 @@ using tfa::FwdCfg;
 using tfa::FwdParams;
 
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_last_variant{0};         // kernel the last forward launch used (0 classic, 4 persist, 5 persist64)
 unsigned long long* g_trace_buf = nullptr;   // only read by -DTFA_TRACE variant builds
 int g_trace_block = 0;
 
@@ -149,20 +150,36 @@ int num_sms() {
   return v;
 }
 
-// Kernel selection.  TFA_KERNEL (read once): unset / "classic" = one CTA per work item (fa_fwd_sm100.cuh);
+// Kernel selection.  TFA_KERNEL (read once) forces one kernel: "classic" = one CTA per work item (fa_fwd_sm100.cuh);
 // "persist" = persistent CTAs with cross-item overlap and the TMA-store epilogue (fa_fwd_sm100_persist.cuh);
 // "persist64" = persist for D=128 and the two-warpgroups-per-tile kernel (fa_fwd_sm100_d64.cuh) for D=64.
+// Unset = AUTO, from the B200 measurements of round 2 (profiles/r02_kernel_choice.md): see choose_kernel().
 // The round-1 experimental variants (column-split softmax, the first persistent kernel and its port) were measured on
 // B200 in round 2 -- 8-20 % slower than the classic kernel or faulting -- and removed (profiles/r02_variants_ab.txt).
+enum { KV_AUTO = -1, KV_CLASSIC = 0, KV_PERSIST = 4, KV_PERSIST64 = 5 };
 int kernel_variant() {
   static int v = [] {
     const char* e = std::getenv("TFA_KERNEL");
-    if (e == nullptr) return 0;
-    if (std::strcmp(e, "persist") == 0) return 4;
-    if (std::strcmp(e, "persist64") == 0) return 5;
-    return 0;
+    if (e == nullptr) return static_cast<int>(KV_AUTO);
+    if (std::strcmp(e, "classic") == 0) return static_cast<int>(KV_CLASSIC);
+    if (std::strcmp(e, "persist") == 0) return static_cast<int>(KV_PERSIST);
+    if (std::strcmp(e, "persist64") == 0) return static_cast<int>(KV_PERSIST64);
+    return static_cast<int>(KV_AUTO);
   }();
   return v;
+}
+// AUTO: the persistent kernel wins where its cross-item overlap and TMA-store epilogue outweigh its slightly longer
+// issue path (rolled issuer, dynamic ring slots): many work items per SM, non-causal items, and the fused exchange
+// (peer stores leave from the TMA engine instead of the softmax warps).  Few, long, lopsided (causal) items per SM are
+// where the one-CTA-per-item kernel's hardware scheduling still wins by ~2 %.
+int choose_kernel(int D, bool causal, long long nitems, long long npairs, int sms, int n_extra) {
+  const int forced = kernel_variant();
+  if (forced != KV_AUTO) return forced;
+  if (D != 128) return KV_CLASSIC;
+  if (n_extra > 0) return KV_PERSIST;
+  if (!causal) return KV_PERSIST;
+  // causal: few very long items per SM (S >= 8192 with < 32 items per SM) still favour the classic kernel by ~2 %
+  return (npairs >= 32 && nitems < 32LL * sms) ? KV_CLASSIC : KV_PERSIST;
 }
 
 // cudaFuncSetAttribute is per device (context) and costs well under a microsecond: set it on every launch instead of
@@ -174,9 +191,9 @@ cudaError_t opt_in_smem(K kernel, int bytes) {
 
 template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
 int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const tfa::OutMaps& to, FwdParams p,
-                long long nitems, cudaStream_t stream) {
+                long long nitems, int variant, cudaStream_t stream) {
   cudaError_t cerr = cudaSuccess;
-  const int variant = kernel_variant();
+  g_last_variant.store((variant == 5 && D != 64) ? 4 : variant, std::memory_order_relaxed);
   if (variant == 4 || variant == 5) {
     int slot = 0;
     p.sched_counter = acquire_sched_counter(stream, &cerr, &slot, true);
@@ -212,8 +229,8 @@ int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 
 template <int D>
 int dispatch(bool causal, bool bf16, bool f32, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-             const tfa::OutMaps& to, const FwdParams& p, long long nblocks, cudaStream_t s) {
-#define TFA_GO(C_, B_, F_) return launch_inst<D, C_, B_, F_>(tq, tk, tv, to, p, nblocks, s)
+             const tfa::OutMaps& to, const FwdParams& p, long long nblocks, int variant, cudaStream_t s) {
+#define TFA_GO(C_, B_, F_) return launch_inst<D, C_, B_, F_>(tq, tk, tv, to, p, nblocks, variant, s)
   if (causal) {
     if (bf16) { if (f32) TFA_GO(true, true, true); else TFA_GO(true, true, false); }
     else      { if (f32) TFA_GO(true, false, true); else TFA_GO(true, false, false); }
@@ -330,7 +347,7 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
   const bool plain = (a.Sq == a.Sk) && (a.Hq == a.Hkv);
   if (n_extra > 0) {
     // fused exchange: 16-bit output of the reference-shaped problem only
-    if (n_extra > 7 || extra_dst == nullptr || f32 || (kernel_variant() != 0 && kernel_variant() < 4) || !plain || a.num_splits > 1)
+    if (n_extra > 7 || extra_dst == nullptr || f32 || !plain || a.num_splits > 1)
       return TFA_EINVAL_SHAPE;
     for (int i = 0; i < n_extra; ++i)
       if (extra_dst[i] == nullptr || (reinterpret_cast<uintptr_t>(extra_dst[i]) & 15u)) return TFA_EINVAL_PTR;
@@ -376,12 +393,15 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
   if ((rc = make_tmap(&tk, a.k, a.dtype, a.D, a.Sk, a.B, a.Hkv, a.ksb, a.ksh, a.kss))) return rc;
   if ((rc = make_tmap(&tv, a.v, a.dtype, a.D, a.Sk, a.B, a.Hkv, a.ksb, a.ksh, a.kss))) return rc;
 
-  // output tensor maps of the persistent kernel's TMA-store epilogue (16-bit output only): [0] = out, [1..] = peers
+  const long long npairs_l = (static_cast<long long>(a.Sq) + 255) / 256;
+  const long long nitems_l = npairs_l * a.B * a.Hq * nsplit;
+  const int variant = choose_kernel(a.D, causal, nitems_l, npairs_l, num_sms(), n_extra);
+  // output tensor maps of the persistent kernels' TMA-store epilogue (16-bit output only): [0] = out, [1..] = peers
   tfa::OutMaps to;
   std::memset(&to, 0, sizeof(to));
-  if (kernel_variant() >= 4 && !f32 && nsplit == 1) {
+  if (variant >= KV_PERSIST && !f32 && nsplit == 1) {
     // store box: 32 rows x 64 columns (SWIZZLE_128B); the D=64 two-warpgroup kernel stores 32 x 32 (SWIZZLE_64B)
-    const int bc = (kernel_variant() == 5 && a.D == 64) ? 32 : 64;
+    const int bc = (variant == KV_PERSIST64 && a.D == 64) ? 32 : 64;
     if ((rc = make_tmap(&to.m[0], a.out, a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss, 32, bc))) return rc;
     for (int i = 0; i < n_extra; ++i)
       if ((rc = make_tmap(&to.m[1 + i], extra_dst[i], a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss, 32, bc))) return rc;
@@ -440,8 +460,8 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
   p.total_items = static_cast<int>(nitems);
   p.sched_counter = nullptr;
   const bool kernel_f32 = f32 || nsplit > 1;
-  if (a.D == 64) rc = dispatch<64>(causal, bf16, kernel_f32, tq, tk, tv, to, p, nitems, stream);
-  else           rc = dispatch<128>(causal, bf16, kernel_f32, tq, tk, tv, to, p, nitems, stream);
+  if (a.D == 64) rc = dispatch<64>(causal, bf16, kernel_f32, tq, tk, tv, to, p, nitems, variant, stream);
+  else           rc = dispatch<128>(causal, bf16, kernel_f32, tq, tk, tv, to, p, nitems, variant, stream);
   if (rc) return rc;
 
   if (nsplit > 1) {
@@ -632,6 +652,8 @@ void tfa_host_release(void) {
 }
 
 unsigned long long tfa_launch_count(void) { return g_launches.load(); }
+// development aid (not in the public header): which kernel the last forward launch used (0 classic, 4 persist, 5 d64)
+int tfa_internal_last_variant(void) { return g_last_variant.load(); }
 // exported for the self tests living in another translation unit
 void tfa_internal_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void* tfa_internal_dbg_dev(void) { init_dbg(); return g_dbg_dev; }
