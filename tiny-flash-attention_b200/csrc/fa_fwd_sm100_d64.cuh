@@ -34,7 +34,7 @@ struct P64Cfg {
   static constexpr int STG_BYTES = 16 * STG_WARP_BYTES;
   static constexpr int XCH_BYTES = 2 * 128 * 2 * 8;                 // [tile][row][half] {m, l}
   static constexpr uint32_t Q_FULL = 0, Q_EMPTY = 2, KV_FULL = 4, KV_EMPTY = KV_FULL + NSTAGE, S_FULL = KV_EMPTY + NSTAGE,
-                            P_HALF = S_FULL + 2, P_FULL = P_HALF + 4, O_FULL = P_FULL + 4, SCHED_FULL = O_FULL + 2,
+                            P_HALF = S_FULL + 2, P_FULL = P_HALF + 2, O_FULL = P_FULL + 2, SCHED_FULL = O_FULL + 2,
                             SCHED_EMPTY = SCHED_FULL + 2, NUM_BARS = SCHED_EMPTY + 2;
   static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES + NSTAGE * TILE_BYTES + STG_BYTES + XCH_BYTES + NUM_BARS * 8 + 32;
   static constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;          // O_{t,h} at TM_O + (2t+h)*64
@@ -86,9 +86,9 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       mbar_init(bar(C::SCHED_FULL, t), 1);
       mbar_init(bar(C::SCHED_EMPTY, t), 17);   // UMMA warp + 16 softmax warps
     }
-    for (uint32_t i = 0; i < 4; ++i) {
-      mbar_init(bar(C::P_HALF, i), 4);         // one arrival per warp of warpgroup (t, h), i = 2t + h
-      mbar_init(bar(C::P_FULL, i), 4);
+    for (uint32_t t = 0; t < 2; ++t) {
+      mbar_init(bar(C::P_HALF, t), 8);         // one arrival per warp of BOTH half-warpgroups of tile t: the issuer pays
+      mbar_init(bar(C::P_FULL, t), 8);         // two waits per tile, not four (its fixed costs dominate at D=64)
     }
     for (uint32_t i = 0; i < NSTAGE; ++i) {
       mbar_init(bar(C::KV_FULL, i), 1);
@@ -285,7 +285,11 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           // the 8-deep ring is far ahead: these waits are satisfied except right behind an item boundary
           mbar_wait(bar(C::KV_FULL, vslot), ent_par(ev), p.dbg, SITE_MMA_V);
           if (j + 1 < nmax) mbar_wait(bar(C::KV_FULL, kslot), ent_par(ek), p.dbg, SITE_MMA_K);
+#if TFA_ISSUER_UNROLL_T
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
           for (int t = 0; t < 2; ++t) {
             const int nt = (t == 0) ? n0 : n1;
             const int no = (t == 0) ? n1 : n0;
@@ -295,18 +299,14 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             const bool has_next = (j + 1 < nt);
             if (active) {
               const uint32_t ppar = (st >> (2 + t)) & 1u;
-              mbar_wait(bar(C::P_HALF, 2 * t), ppar, p.dbg, SITE_MMA_PH);
+              mbar_wait(bar(C::P_HALF, t), ppar, p.dbg, SITE_MMA_PH);
               tc_fence_after();
               issue_PV(t, 0, vslot, j > 0, 0, 2, false, false);
-              mbar_wait(bar(C::P_HALF, 2 * t + 1), ppar, p.dbg, SITE_MMA_PH);
-              tc_fence_after();
               issue_PV(t, 1, vslot, j > 0, 0, 2, false, false);
-              mbar_wait(bar(C::P_FULL, 2 * t), ppar, p.dbg, SITE_MMA_P);
-              tc_fence_after();
-              issue_PV(t, 0, vslot, true, 2, 4, false, false);
-              mbar_wait(bar(C::P_FULL, 2 * t + 1), ppar, p.dbg, SITE_MMA_P);
+              mbar_wait(bar(C::P_FULL, t), ppar, p.dbg, SITE_MMA_P);
               st ^= (1u << (2 + t));
               tc_fence_after();
+              issue_PV(t, 0, vslot, true, 2, 4, false, false);
               issue_PV(t, 1, vslot, true, 2, 4, last_v_user, !has_next);
             }
             // ONE S site (instruction-cache footprint, see fa_fwd_sm100_persist.cuh): next KV tile, or the hoisted first
@@ -491,7 +491,7 @@ fa_fwd_sm100_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(qt == 0 ? C::P_HALF : C::P_FULL, 2 * t + h));
+          if (lane == 0) mbar_arrive(bar(qt == 0 ? C::P_HALF : C::P_FULL, t));
         }
         acc0 = fadd2(acc0, acc1);
         l += acc0.x + acc0.y;

@@ -175,9 +175,9 @@ int kernel_variant() {
 int choose_kernel(int D, bool causal, long long nitems, long long npairs, int sms, int n_extra) {
   const int forced = kernel_variant();
   if (forced != KV_AUTO) return forced;
-  if (D != 128) return KV_CLASSIC;
   if (n_extra > 0) return KV_PERSIST;
-  if (!causal) return KV_PERSIST;
+  if (!causal) return KV_PERSIST;          // D=64 too: +5..14 % (cfg2 0.1106 vs 0.1167 ms, B16 H16 S1024 0.1024 vs 0.1167)
+  if (D != 128) return KV_CLASSIC;         // D=64 causal: classic by 5-9 % (B4 H32 S4096 0.387 vs 0.408 ms)
   // causal: few very long items per SM (S >= 8192 with < 32 items per SM) still favour the classic kernel by ~2 %
   return (npairs >= 32 && nitems < 32LL * sms) ? KV_CLASSIC : KV_PERSIST;
 }
