@@ -9,8 +9,8 @@ for v in $VARIANTS; do
   [ "$v" = "default" ] && unset TFA_KERNEL || export TFA_KERNEL=$v
   timeout 600 python -m pytest tests/test_multi_gpu.py tests/test_multi_device.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/m${N}_test_$v.log 2>&1
   echo "multi-gpu tests [$v] rc=$?"; tail -4 gpurun_out/m${N}_test_$v.log
-  for ex in fused nccl; do
-    [ "$ex" = "nccl" ] && [ "$v" != "default" ] && continue
+  for ex in fused ${NCCL_ARM:-nccl}; do
+    [ "$ex" = "none" ] && continue; [ "$ex" = "nccl" ] && [ "$v" != "default" ] && continue
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 10 --warmup 3 --exchange $ex > gpurun_out/m${N}_bench_${v}_$ex.json 2> gpurun_out/m${N}_bench_${v}_$ex.err
     echo "bench N=$N [$v] $ex rc=$?"; python - <<PY
 import json
