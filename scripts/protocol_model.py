@@ -36,20 +36,20 @@ class Bar:
 
 
 class Sim:
-    def __init__(self, items, nstage, rng, hoist=True):
-        self.items, self.N, self.rng, self.hoist = items, nstage, rng, hoist     # items: list of (n0, n1)
+    def __init__(self, items, nstage, rng, hoist=True, two=False):
+        self.items, self.N, self.rng, self.hoist, self.two = items, nstage, rng, hoist, two     # items: list of (n0, n1)
         B = lambda n, c: Bar(n, c)
         self.q_full = [B(f"q_full{t}", 1) for t in range(2)]
         self.q_empty = [B(f"q_empty{t}", 1) for t in range(2)]
         self.kv_full = [B(f"kv_full{i}", 1) for i in range(nstage)]
-        self.kv_empty = [B(f"kv_empty{i}", 1) for i in range(nstage)]
+        self.kv_empty = [B(f"kv_empty{i}", 2 if two else 1) for i in range(nstage)]
         self.s_full = [B(f"s_full{t}", 1) for t in range(2)]
         self.p_half = [B(f"p_half{t}", 1) for t in range(2)]      # (the 4 warps of a warpgroup arrive together: count 1 here)
         self.p_3q = [B(f"p_3q{t}", 1) for t in range(2)]
         self.p_full = [B(f"p_full{t}", 1) for t in range(2)]
         self.o_full = [B(f"o_full{t}", 1) for t in range(2)]
         self.sched_full = [B(f"sched_full{i}", 1) for i in range(2)]
-        self.sched_empty = [B(f"sched_empty{i}", 3) for i in range(2)]   # issuer + 2 warpgroups
+        self.sched_empty = [B(f"sched_empty{i}", 4 if two else 3) for i in range(2)]   # issuer(s) + 2 warpgroups
         self.sched_ring = [None, None]
         # shadow state
         self.q_buf = [None, None]            # (item, t) resident (after TMA completion)
@@ -287,6 +287,105 @@ class Sim:
             cur = nxt
             k += 1
 
+    def issuer2(self, t):
+        """The two-issuer variant (one issuer per tile, K/V entries released by count) that was measured 28 % slower on B200 and
+        removed from the kernel in r02; its protocol is kept here because it is the simpler one to reason about."""
+        total, N = len(self.items), self.N
+        slot_of = lambda e: e % N
+        par_of = lambda e: (e // N) & 1
+        ent_base, k, qpar, ppar = 0, 0, 0, 0
+
+        def S(item, j, e, release_q):
+            kslot = slot_of(e)
+            self.q_readers[t] += 1
+            self.kv_readers[kslot] += 1
+
+            def start():
+                assert self.q_buf[t] == (item, t), f"S{t}(item {item}, j {j}) reads Q buffer holding {self.q_buf[t]}"
+                assert self.kv_buf[kslot] == (item, j, 'K'), f"S{t}(item {item}, j {j}) reads slot {kslot} holding {self.kv_buf[kslot]}"
+                assert not self.S_unread[t], f"S{t}(item {item}, j {j}) overwrites an unread S tile"
+                self.tmem_S[t] = None
+
+            def done():
+                self.q_readers[t] -= 1
+                self.kv_readers[kslot] -= 1
+                self.tmem_S[t] = ('S', item, j)
+                self.S_unread[t] = True
+                self.s_full[t].arrive()
+                self.kv_empty[kslot].arrive()
+                if release_q:
+                    self.q_empty[t].arrive()
+            self.mma(start, done)
+
+        def PV(item, j, e, part, release, done_bar):
+            vslot = slot_of(e)
+            self.kv_readers[vslot] += 1
+            self.P_readers[t] += 1
+
+            def start():
+                assert self.kv_buf[vslot] == (item, j, 'V'), f"PV{t}(item {item}, j {j}) reads slot {vslot} holding {self.kv_buf[vslot]}"
+                ts = self.tmem_S[t]
+                assert ts is not None and ts[0] == 'P' and ts[1:3] == (item, j) and ts[3] >= part, f"PV{t}(item {item}, j {j}, part {part}) reads P = {ts}"
+                if part == 1:
+                    if j == 0:
+                        assert not self.O_unread[t], f"PV{t}(item {item}) overwrites an unread O tile"
+                        self.O_state[t] = (item, 0)
+                    assert self.O_state[t] == (item, j)
+
+            def done():
+                self.kv_readers[vslot] -= 1
+                self.P_readers[t] -= 1
+                if part == 3:
+                    self.O_state[t] = (item, j + 1)
+                if release:
+                    self.kv_empty[vslot].arrive()
+                if done_bar:
+                    self.O_unread[t] = True
+                    self.o_full[t].arrive()
+            self.mma(start, done)
+
+        def pass_entry(e):
+            yield lambda: self.kv_full[slot_of(e)].done(par_of(e))
+            self.kv_empty[slot_of(e)].arrive()
+
+        cur = yield from self.sched_get(0)
+        while cur < total:
+            n = self.items[cur]
+            nt, nmax = n[t], max(n)
+            if nt > 0:
+                yield lambda: self.q_full[t].done(qpar)
+                qpar ^= 1
+                yield lambda: self.kv_full[slot_of(ent_base)].done(par_of(ent_base))
+                S(cur, 0, ent_base, nt == 1)
+            else:
+                yield from pass_entry(ent_base)
+            for j in range(nmax):
+                ev, ek = ent_base + 2 * j + 1, ent_base + 2 * j + 2
+                k_exists = j + 1 < nmax
+                if j < nt:
+                    has_next = j + 1 < nt
+                    yield lambda: self.kv_full[slot_of(ev)].done(par_of(ev))
+                    if has_next:
+                        yield lambda: self.kv_full[slot_of(ek)].done(par_of(ek))
+                    yield lambda: self.p_half[t].done(ppar)
+                    PV(cur, j, ev, 1, False, False)
+                    yield lambda: self.p_3q[t].done(ppar)
+                    PV(cur, j, ev, 2, False, False)
+                    yield lambda: self.p_full[t].done(ppar)
+                    ppar ^= 1
+                    PV(cur, j, ev, 3, True, not has_next)
+                    if has_next:
+                        S(cur, j + 1, ek, j + 2 == nt)
+                    elif k_exists:
+                        yield from pass_entry(ek)
+                else:
+                    yield from pass_entry(ev)
+                    if k_exists:
+                        yield from pass_entry(ek)
+            ent_base += 2 * nmax
+            cur = yield from self.sched_get(k + 1)
+            k += 1
+
     def softmax(self, t):
         total = len(self.items)
         scnt = ocnt = 0
@@ -320,7 +419,11 @@ class Sim:
             self.stored[key] = n
 
     def run(self, max_steps=2_000_000):
-        roles = {"producer": self.producer(), "issuer": self.issuer(), "sm0": self.softmax(0), "sm1": self.softmax(1)}
+        if self.two:
+            roles = {"producer": self.producer(), "issuer0": self.issuer2(0), "issuer1": self.issuer2(1),
+                     "sm0": self.softmax(0), "sm1": self.softmax(1)}
+        else:
+            roles = {"producer": self.producer(), "issuer": self.issuer(), "sm0": self.softmax(0), "sm1": self.softmax(1)}
         waiting = {}
         for name, g in roles.items():
             try:
@@ -384,7 +487,7 @@ def main():
         items = random_items(rng)
         nstage = rng.choice([4, 8])
         try:
-            Sim(items, nstage, rng, hoist=rng.random() < 0.8).run()
+            Sim(items, nstage, rng, hoist=rng.random() < 0.8, two=(trial % 2 == 1)).run()
         except AssertionError as e:
             print(f"VIOLATION trial {trial} seed {seed0} nstage {nstage} items {items}: {e}")
             sys.exit(1)

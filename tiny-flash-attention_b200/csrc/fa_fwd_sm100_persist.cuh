@@ -24,6 +24,7 @@
 // (register donors: setmaxnreg works on warpgroups).
 #pragma once
 #include "fa_fwd_sm100.cuh"
+#include <type_traits>
 
 namespace tfa {
 
@@ -77,6 +78,9 @@ struct PItem {
 // while the other tile finishes -- a head start of most of a step.  Alternating which tile RESOURCE (t = 0 / 1: Q
 // buffer, S/O columns, barriers, warpgroup) gets the long row block from one item of the CTA to the next hands that head
 // start to the long tile every time (`swap` = odd CTA-local item number).  -DTFA_ALTERNATE=0 disables (A/B).
+// (Measured in r02 and removed: TWO UMMA issuer warps, one per Q tile, K/V entries released by count.  Parity-green and
+//  simpler -- no hoist probe, no last-user bookkeeping -- but 28 % SLOWER on B200 (cfg3 0.575 vs 0.449 ms): tcgen05.mma
+//  streams issued by two warps do not overlap in the tensor pipe the way one warp's in-order stream does.)
 #ifndef TFA_ISSUER_UNROLL_T
 #define TFA_ISSUER_UNROLL_T 1   // the issuer's main loop is unrolled over the two tiles: compile-time tile index on the issue
                                 // path; measured +3 % over the rolled loop once the item number was warp-uniform (r02)
@@ -644,6 +648,16 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         const float2 c2 = make_float2(c, c);
         const float2 nm2 = make_float2(-m_ref * c, -m_ref * c);
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#ifndef TFA_DEFER_HANDOFF
+#define TFA_DEFER_HANDOFF 0   // 1: the drain of quarter q's TMEM stores (tcgen05.wait::st, ~100+ cycles in which the warp
+                              // issues nothing) is taken AFTER quarter q+1's exponentials; a fake register dependency on
+                              // the wait keeps ptxas from sinking the exponentials back below it (r01 tried without one)
+#endif
+        auto hand_off = [&](int which) {       // which: 1 = p_half, 2 = p_3q, 3 = p_full
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(which == 1 ? C::P_HALF : (which == 2 ? C::P_3Q : C::P_FULL), t));
+        };
 #pragma unroll
         for (int qt = 0; qt < 4; ++qt) {
           uint32_t pk[16];
@@ -661,14 +675,25 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
             pk[i] = pack_16x2<IS_BF16>(e.x, e.y);
           }
+#if TFA_DEFER_HANDOFF
+          if (qt >= 2) {       // quarters 0..qt-1 are stored; their drain was deferred to here, behind this quarter's math
+            asm volatile("tcgen05.wait::st.sync.aligned; // after %0" ::"r"(pk[15]) : "memory");
+            hand_off(qt - 1);
+            TFA_PTRACE_SM(5);
+          }
+          tmem_st_x16(tP + qt * 16, pk);
+          if (qt == 3) {
+            tmem_wait_st();
+            hand_off(3);
+          }
+#else
           tmem_st_x16(tP + qt * 16, pk);
           if (qt >= 1) {       // hand-offs after keys 0..63 (p_half), 64..95 (p_3q), 96..127 (p_full)
             tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(qt == 1 ? C::P_HALF : (qt == 2 ? C::P_3Q : C::P_FULL), t));
+            hand_off(qt);
             if (qt < 3) TFA_PTRACE_SM(5);
           }
+#endif
         }
         acc0 = fadd2(acc0, acc1);
         l += acc0.x + acc0.y;
