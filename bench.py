@@ -642,8 +642,7 @@ def kernel_name(tfa):
     except Exception:  # noqa: BLE001
         v = 0
     return {0: "fa_fwd_sm100_kernel<128,causal,bf16> (one CTA per work item)",
-            4: "fa_fwd_sm100_persist_kernel<128,causal,bf16> (persistent, TMA-store epilogue)",
-            5: "fa_fwd_sm100_d64_kernel"}.get(v, str(v))
+            4: "fa_fwd_sm100_persist_kernel<128,causal,bf16> (persistent, TMA-store epilogue)"}.get(v, str(v))
 
 
 

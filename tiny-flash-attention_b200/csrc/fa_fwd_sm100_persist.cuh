@@ -42,13 +42,7 @@ struct PCfg {
   static constexpr int NSTAGE = (D == 128) ? 4 : 8;                 // K/V ring depth (tiles), power of two
   static constexpr int NSTAGE_LOG2 = (D == 128) ? 2 : 3;
   static constexpr int STG_WARP_BYTES = 32 * 128;                   // epilogue staging: 32 rows x 128 B per softmax warp
-#ifndef TFA_BISECT_NOSTG
-#define TFA_BISECT_NOSTG 0    // experiment (one-item mode only): no staging buffer, the epilogue stages in the dead Q tiles
-#endif
-#ifndef TFA_BISECT_NOSCHED
-#define TFA_BISECT_NOSCHED 0  // experiment (one-item mode only): no scheduler ring, item = blockIdx.x
-#endif
-  static constexpr int STG_BYTES = TFA_BISECT_NOSTG ? 0 : 8 * STG_WARP_BYTES;
+  static constexpr int STG_BYTES = 8 * STG_WARP_BYTES;
   // barrier table (index of the first barrier of each kind)
   static constexpr uint32_t Q_FULL = 0, Q_EMPTY = 2, KV_FULL = 4, KV_EMPTY = KV_FULL + NSTAGE, S_FULL = KV_EMPTY + NSTAGE,
                             P_HALF = S_FULL + 2, P_3Q = P_HALF + 2, P_FULL = P_3Q + 2, O_FULL = P_FULL + 2,
@@ -73,26 +67,19 @@ struct PItem {
   int nmax;
 };
 
-// Causal items are lopsided: the lower 128 rows see one KV tile more than the upper ones, and an item lasts as long as
-// its LONG tile's serial chain.  The tile that finishes first hoists its next first S and pre-computes that softmax
-// while the other tile finishes -- a head start of most of a step.  Alternating which tile RESOURCE (t = 0 / 1: Q
-// buffer, S/O columns, barriers, warpgroup) gets the long row block from one item of the CTA to the next hands that head
-// start to the long tile every time (`swap` = odd CTA-local item number).  -DTFA_ALTERNATE=0 disables (A/B).
-// (Measured in r02 and removed: TWO UMMA issuer warps, one per Q tile, K/V entries released by count.  Parity-green and
-//  simpler -- no hoist probe, no last-user bookkeeping -- but 28 % SLOWER on B200 (cfg3 0.575 vs 0.449 ms): tcgen05.mma
-//  streams issued by two warps do not overlap in the tensor pipe the way one warp's in-order stream does.)
+// Tuning switches (A/B builds: build.py --variant NAME -DSWITCH=v).  Measured in r02 and reverted: alternating the long
+// causal tile between the two tile resources from item to item (-8 %), two UMMA issuer warps (-28 %), a rolled issuer loop
+// over the tile index (-3 %), no L2 prefetch of the next Q tiles (-3 %), deferring the P hand-offs behind the next quarter's
+// exponentials (0 %, kept behind TFA_DEFER_HANDOFF).
 #ifndef TFA_ISSUER_UNROLL_T
-#define TFA_ISSUER_UNROLL_T 1   // the issuer's main loop is unrolled over the two tiles: compile-time tile index on the issue
-                                // path; measured +3 % over the rolled loop once the item number was warp-uniform (r02)
+#define TFA_ISSUER_UNROLL_T 1   // the issuer's main loop is unrolled over the two tiles: compile-time tile index on the issue path
 #endif
 #ifndef TFA_HOIST
-#define TFA_HOIST 1          // 0: never issue the next item's first S early (A/B)
+#define TFA_HOIST 1             // 0: never issue the next item's first S early
 #endif
-#ifndef TFA_ALTERNATE
-#define TFA_ALTERNATE 0
-#endif
+
 template <bool CAUSAL>
-__device__ __forceinline__ PItem decode_pitem(int item, const FwdParams& p, bool swap = false) {
+__device__ __forceinline__ PItem decode_pitem(int item, const FwdParams& p) {
   PItem w;
   int pr;
   decode_work(item, p.npairs, p.nsplit, p.head_chunk, p.BH, w.bh, w.split, pr);
@@ -109,10 +96,6 @@ __device__ __forceinline__ PItem decode_pitem(int item, const FwdParams& p, bool
     w.nblk[t] = max(0, min(nfull - w.jb, p.split_tiles));
   }
   w.nmax = max(w.nblk[0], w.nblk[1]);
-  if (TFA_ALTERNATE && CAUSAL && swap) {
-    int x = w.row0[0]; w.row0[0] = w.row0[1]; w.row0[1] = x;
-    x = w.nblk[0]; w.nblk[0] = w.nblk[1]; w.nblk[1] = x;
-  }
   return w;
 }
 
@@ -246,7 +229,6 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 
   // consumer side of the scheduler ring: the k-th item handed to this CTA lives in slot k&1 (>= total: no more work)
   auto sched_get = [&](int k) -> int {
-    if (TFA_BISECT_NOSCHED) return k == 0 ? static_cast<int>(blockIdx.x) : total;
     mbar_wait(bar(C::SCHED_FULL, k & 1), (k >> 1) & 1, p.dbg, SITE_P_SCHED_FULL);
     // REDUX makes the item number PROVABLY warp-uniform for the compiler.  Without it everything derived from a value
     // loaded from shared memory (tile counts, loop bounds, ring slots, barrier parities, MMA descriptors) is treated as
@@ -266,21 +248,10 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       // next non-empty work item (a split-KV item wholly above the causal diagonal has no tiles: never handed out)
       // p.sched_counter = {next item, CTAs that ran out of work}: both are 0 at launch, and the last CTA to draw the
       // terminator puts them back to 0 for the next launch that is handed this pair (no memset in front of each launch)
-#ifndef TFA_ONE_ITEM
-#define TFA_ONE_ITEM 0       // experiment: every CTA takes exactly one item (grid = number of items)
-#endif
       int fetched = 0;
       auto fetch = [&]() -> int {
         for (;;) {
-          if (TFA_ONE_ITEM && fetched) {
-            if (atomicAdd(p.sched_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
-              p.sched_counter[0] = 0;
-              p.sched_counter[1] = 0;
-            }
-            return total;
-          }
           ++fetched;
-          if (TFA_BISECT_NOSCHED) return static_cast<int>(blockIdx.x);
           // CTA c starts with item c (no atomic, no ~1500-cycle round trip in front of the first load); the counter hands
           // out the items from gridDim.x on
           const int i = (fetched == 1) ? static_cast<int>(blockIdx.x) : atomicAdd(p.sched_counter, 1) + static_cast<int>(gridDim.x);
@@ -298,7 +269,6 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       // release/acquire for generic shared-memory accesses.  st.async, which would carry data and signal together, is
       // an illegal instruction outside a cluster launch on sm_100a -- measured.)
       auto publish = [&](int k, int item) {
-        if (TFA_BISECT_NOSCHED) return;
         mbar_wait(bar(C::SCHED_EMPTY, k & 1), ((k >> 1) & 1) ^ 1, p.dbg, SITE_P_SCHED_EMPTY);
         sched_ring[k & 1] = item;
         mbar_arrive(bar(C::SCHED_FULL, k & 1));     // release: the store above is visible to the waiters (acquire in try_wait)
@@ -311,7 +281,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       int cur = fetch();
       publish(0, cur);
       while (cur < total) {
-        const PItem w = decode_pitem<CAUSAL>(cur, p, k & 1);
+        const PItem w = decode_pitem<CAUSAL>(cur, p);
         auto load_q = [&](int t) {
           if (w.nblk[t] > 0) {
             mbar_wait(bar(C::Q_EMPTY, t), ((qpar >> t) & 1u) ^ 1u, p.dbg, SITE_P_QEMPTY);
@@ -408,7 +378,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       while (cur < total) {
         int n0, n1;
         {
-          const PItem x = decode_pitem<CAUSAL>(cur, p, k & 1);
+          const PItem x = decode_pitem<CAUSAL>(cur, p);
           n0 = x.nblk[0];
           n1 = x.nblk[1];
         }
@@ -446,7 +416,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           if (!block && !__all_sync(0xffffffffu, mbar_test_wait(bar(C::SCHED_FULL, (k + 1) & 1), ((k + 1) >> 1) & 1))) return;
           nxt = sched_get(k + 1);
           if (nxt < total) {
-            const PItem x = decode_pitem<CAUSAL>(nxt, p, (k + 1) & 1);
+            const PItem x = decode_pitem<CAUSAL>(nxt, p);
             nn0 = x.nblk[0];
             nn1 = x.nblk[1];
           }
@@ -550,8 +520,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     const uint32_t tP = tS;
     const float c = p.scale_log2;
     const int S = p.S, Sk = p.Sk;
-    const uint32_t stg = TFA_BISECT_NOSTG ? (sQ_addr + t * TILE + (warp & 3) * C::STG_WARP_BYTES)
-                                          : (smem_u32(sStg) + warp * C::STG_WARP_BYTES);   // this warp's private staging (1024-aligned)
+    const uint32_t stg = smem_u32(sStg) + warp * C::STG_WARP_BYTES;   // this warp's private staging (1024-aligned)
 
     TFA_TRACE_DECL(t)
 #ifdef TFA_TRACE
@@ -566,7 +535,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     for (int k = 0;; ++k) {
       const int item = sched_get(k);
       if (item >= total) break;
-      const PItem w = decode_pitem<CAUSAL>(item, p, k & 1);
+      const PItem w = decode_pitem<CAUSAL>(item, p);
       const int n = (t == 0) ? w.nblk[0] : w.nblk[1];
       if (n == 0) continue;
       const int trow0 = (t == 0) ? w.row0[0] : w.row0[1];
@@ -577,17 +546,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
       float l = 0.f;       // running sum of exp2((s - m_ref) * c)
 
       for (int j = 0; j < n; ++j) {
-#if defined(TFA_SM_WAIT_HINT)
-        {
-          uint32_t ok = 0;
-          while (!ok) {
-            asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}"
-                         : "=r"(ok) : "r"(bar(C::S_FULL, t)), "r"(scnt & 1u), "r"(1000000u) : "memory");
-          }
-        }
-#else
         mbar_wait(bar(C::S_FULL, t), scnt & 1u, p.dbg, SITE_SM_S);
-#endif
         TFA_PTRACE_SM(2);
         tc_fence_after();
 

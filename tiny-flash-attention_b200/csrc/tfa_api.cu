@@ -10,7 +10,6 @@
 #include "../../include/tfa_b200.h"
 #include "fa_fwd_sm100.cuh"
 #include "fa_fwd_sm100_persist.cuh"
-#include "fa_fwd_sm100_d64.cuh"
 #include "fa_splitkv_combine.cuh"
 
 #include <cuda_runtime.h>
@@ -28,7 +27,7 @@ using tfa::FwdCfg;
 using tfa::FwdParams;
 
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_last_variant{0};         // kernel the last forward launch used (0 classic, 4 persist, 5 persist64)
+std::atomic<int> g_last_variant{0};         // kernel the last forward launch used (0 classic, 4 persistent)
 unsigned long long* g_trace_buf = nullptr;   // only read by -DTFA_TRACE variant builds
 int g_trace_block = 0;
 
@@ -152,18 +151,17 @@ int num_sms() {
 
 // Kernel selection.  TFA_KERNEL (read once) forces one kernel: "classic" = one CTA per work item (fa_fwd_sm100.cuh);
 // "persist" = persistent CTAs with cross-item overlap and the TMA-store epilogue (fa_fwd_sm100_persist.cuh);
-// "persist64" = persist for D=128 and the two-warpgroups-per-tile kernel (fa_fwd_sm100_d64.cuh) for D=64.
 // Unset = AUTO, from the B200 measurements of round 2 (profiles/r02_kernel_choice.md): see choose_kernel().
-// The round-1 experimental variants (column-split softmax, the first persistent kernel and its port) were measured on
-// B200 in round 2 -- 8-20 % slower than the classic kernel or faulting -- and removed (profiles/r02_variants_ab.txt).
-enum { KV_AUTO = -1, KV_CLASSIC = 0, KV_PERSIST = 4, KV_PERSIST64 = 5 };
+// The round-1 experimental variants (column-split softmax, the first persistent kernel and its port) and round 2's D=64
+// kernel with two softmax warpgroups per Q tile were measured on B200 -- 5-20 % slower or faulting -- and removed
+// (profiles/r02_variants_ab.txt, profiles/r02_kernel_choice.md).
+enum { KV_AUTO = -1, KV_CLASSIC = 0, KV_PERSIST = 4 };
 int kernel_variant() {
   static int v = [] {
     const char* e = std::getenv("TFA_KERNEL");
     if (e == nullptr) return static_cast<int>(KV_AUTO);
     if (std::strcmp(e, "classic") == 0) return static_cast<int>(KV_CLASSIC);
     if (std::strcmp(e, "persist") == 0) return static_cast<int>(KV_PERSIST);
-    if (std::strcmp(e, "persist64") == 0) return static_cast<int>(KV_PERSIST64);
     return static_cast<int>(KV_AUTO);
   }();
   return v;
@@ -193,27 +191,14 @@ template <int D, bool CAUSAL, bool IS_BF16, bool OUT_F32>
 int launch_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const tfa::OutMaps& to, FwdParams p,
                 long long nitems, int variant, cudaStream_t stream) {
   cudaError_t cerr = cudaSuccess;
-  g_last_variant.store((variant == 5 && D != 64) ? 4 : variant, std::memory_order_relaxed);
-  if (variant == 4 || variant == 5) {
+  g_last_variant.store(variant, std::memory_order_relaxed);
+  if (variant == KV_PERSIST) {
     int slot = 0;
     p.sched_counter = acquire_sched_counter(stream, &cerr, &slot, true);
     if (cerr != cudaSuccess) return static_cast<int>(cerr);
     const int sms = num_sms();
     if (sms <= 0) return TFA_EARCH;
     int nblocks = static_cast<int>(nitems < sms ? nitems : sms);             // one CTA per SM
-#if defined(TFA_ONE_ITEM) && TFA_ONE_ITEM
-    nblocks = static_cast<int>(nitems);                                      // experiment: one item per CTA
-#endif
-    if constexpr (D == 64) {
-      if (variant == 5) {
-        auto kern64 = tfa::fa_fwd_sm100_d64_kernel<CAUSAL, IS_BF16, OUT_F32>;
-        if ((cerr = opt_in_smem(kern64, tfa::P64Cfg::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
-        kern64<<<nblocks, tfa::P64Cfg::THREADS, tfa::P64Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
-        release_sched_counter(slot, stream);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        return static_cast<int>(cudaGetLastError());
-      }
-    }
     auto kern = tfa::fa_fwd_sm100_persist_kernel<D, CAUSAL, IS_BF16, OUT_F32>;
     if ((cerr = opt_in_smem(kern, tfa::PCfg<D>::SMEM_BYTES)) != cudaSuccess) return static_cast<int>(cerr);
     kern<<<nblocks, tfa::PCfg<D>::THREADS, tfa::PCfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
@@ -400,8 +385,7 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
   tfa::OutMaps to;
   std::memset(&to, 0, sizeof(to));
   if (variant >= KV_PERSIST && !f32 && nsplit == 1) {
-    // store box: 32 rows x 64 columns (SWIZZLE_128B); the D=64 two-warpgroup kernel stores 32 x 32 (SWIZZLE_64B)
-    const int bc = (variant == KV_PERSIST64 && a.D == 64) ? 32 : 64;
+    const int bc = 64;       // store box: 32 rows x 64 columns (SWIZZLE_128B)
     if ((rc = make_tmap(&to.m[0], a.out, a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss, 32, bc))) return rc;
     for (int i = 0; i < n_extra; ++i)
       if ((rc = make_tmap(&to.m[1 + i], extra_dst[i], a.dtype, a.D, a.Sq, a.B, a.Hq, a.qsb, a.qsh, a.qss, 32, bc))) return rc;
@@ -652,7 +636,7 @@ void tfa_host_release(void) {
 }
 
 unsigned long long tfa_launch_count(void) { return g_launches.load(); }
-// development aid (not in the public header): which kernel the last forward launch used (0 classic, 4 persist, 5 d64)
+// development aid (not in the public header): which kernel the last forward launch used (0 classic, 4 persistent)
 int tfa_internal_last_variant(void) { return g_last_variant.load(); }
 // exported for the self tests living in another translation unit
 void tfa_internal_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
