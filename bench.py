@@ -384,7 +384,7 @@ def run_ours(args):
     F_job = flops_effective(B, H, S, D)
     value = F_job / t_step / 1e12
 
-    kernel_main = kernel_name(tfa)
+    kernel_main = kernel_name(tfa).replace("_kernel ", "_kernel<128,causal,bf16> ", 1)
     # ---- roofline: the dominant (only) kernel, from the events recorded INSIDE the timed region ----
     k_times = [a_.elapsed_time(b_) * 1e-3 for a_, b_ in kernel_events]
     k_mean, k_min = sum(k_times) / len(k_times), min(k_times)
@@ -641,8 +641,8 @@ def kernel_name(tfa):
         v = int(tfa.lib().tfa_internal_last_variant())
     except Exception:  # noqa: BLE001
         v = 0
-    return {0: "fa_fwd_sm100_kernel<128,causal,bf16> (one CTA per work item)",
-            4: "fa_fwd_sm100_persist_kernel<128,causal,bf16> (persistent, TMA-store epilogue)"}.get(v, str(v))
+    return {0: "fa_fwd_sm100_kernel (one CTA per work item)",
+            4: "fa_fwd_sm100_persist_kernel (persistent, TMA-store epilogue)"}.get(v, str(v))
 
 
 
