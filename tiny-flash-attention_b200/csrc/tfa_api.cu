@@ -170,14 +170,21 @@ int kernel_variant() {
 // issue path (rolled issuer, dynamic ring slots): many work items per SM, non-causal items, and the fused exchange
 // (peer stores leave from the TMA engine instead of the softmax warps).  Few, long, lopsided (causal) items per SM are
 // where the one-CTA-per-item kernel's hardware scheduling still wins by ~2 %.
-int choose_kernel(int D, bool causal, long long nitems, long long npairs, int sms, int n_extra) {
+int choose_kernel(int D, bool causal, long long nitems, long long npairs, long long nkv, int sms, int n_extra) {
   const int forced = kernel_variant();
   if (forced != KV_AUTO) return forced;
   if (n_extra > 0) return KV_PERSIST;
-  if (!causal) return KV_PERSIST;          // D=64 too: +5..14 % (cfg2 0.1106 vs 0.1167 ms, B16 H16 S1024 0.1024 vs 0.1167)
-  if (D != 128) return KV_CLASSIC;         // D=64 causal: classic by 5-9 % (B4 H32 S4096 0.387 vs 0.408 ms)
-  // causal: few very long items per SM (S >= 8192 with < 32 items per SM) still favour the classic kernel by ~2 %
-  return (npairs >= 32 && nitems < 32LL * sms) ? KV_CLASSIC : KV_PERSIST;
+  const bool few_items = nitems < 32LL * sms;
+  if (!causal) {
+    // D=64 too: +5..14 % (cfg2 0.1106 vs 0.1167 ms, B16 H16 S1024 0.1024 vs 0.1167).  Only few items of >= 128 KV tiles
+    // (S >= 16384) favour the classic kernel: D=128 3.00 vs 3.02-3.12 ms, D=64 2.61-2.73 vs 2.73-2.82 (b18 A/B).
+    return (nkv >= 128 && few_items) ? KV_CLASSIC : KV_PERSIST;
+  }
+  // D=64 causal: classic by 4-9 % from S=2048 up (B4 H32 S4096 0.387 vs 0.408 ms), persistent by 7 % on short items
+  // (B32 H32 S512 0.122 vs 0.131)
+  if (D != 128) return npairs <= 2 ? KV_PERSIST : KV_CLASSIC;
+  // causal: few very long items per SM (S >= 8192 with < 32 items per SM) still favour the classic kernel by 2-8 %
+  return (npairs >= 32 && few_items) ? KV_CLASSIC : KV_PERSIST;
 }
 
 // cudaFuncSetAttribute is per device (context) and costs well under a microsecond: set it on every launch instead of
@@ -380,7 +387,8 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
 
   const long long npairs_l = (static_cast<long long>(a.Sq) + 255) / 256;
   const long long nitems_l = npairs_l * a.B * a.Hq * nsplit;
-  const int variant = choose_kernel(a.D, causal, nitems_l, npairs_l, num_sms(), n_extra);
+  const long long nkv_l = split_tiles;   // KV tiles per item
+  const int variant = choose_kernel(a.D, causal, nitems_l, npairs_l, nkv_l, num_sms(), n_extra);
   // output tensor maps of the persistent kernels' TMA-store epilogue (16-bit output only): [0] = out, [1..] = peers
   tfa::OutMaps to;
   std::memset(&to, 0, sizeof(to));
