@@ -36,7 +36,8 @@ class Bar:
 
 
 class Sim:
-    def __init__(self, items, nstage, rng, hoist=True, two=False):
+    def __init__(self, items, nstage, rng, hoist=True, two=False, handoffs=2):
+        self.handoffs = handoffs      # TFA_P_HANDOFFS: 2 (persistent kernel) or 3 (one-CTA-per-item kernel)
         self.items, self.N, self.rng, self.hoist, self.two = items, nstage, rng, hoist, two     # items: list of (n0, n1)
         B = lambda n, c: Bar(n, c)
         self.q_full = [B(f"q_full{t}", 1) for t in range(2)]
@@ -262,8 +263,9 @@ class Sim:
                             if j + 2 < nmax:
                                 yield lambda: self.kv_full[slot_of(ek + 2)].done(par_of(ek + 2))
                             kv_confirmed = True
-                        yield lambda: self.p_3q[t].done(ppar)
-                        issue_PV(cur, t, j, vslot, 2, False, False)
+                        if self.handoffs == 3:
+                            yield lambda: self.p_3q[t].done(ppar)
+                            issue_PV(cur, t, j, vslot, 2, False, False)
                         yield lambda: self.p_full[t].done(ppar)
                         p_par[t] ^= 1
                         issue_PV(cur, t, j, vslot, 3, last_v_user, not has_next)
@@ -408,7 +410,8 @@ class Sim:
                     yield lambda: True                          # (compute; lets other roles interleave)
                     assert self.P_readers[t] == 0 or stage > 1, f"softmax{t} overwrites P while PV reads it"
                     self.tmem_S[t] = ('P', item, j, stage)
-                    barl[t].arrive()
+                    if stage != 2 or self.handoffs == 3 or self.two:
+                        barl[t].arrive()
                 scnt += 1
             yield lambda: self.o_full[t].done(ocnt & 1)
             ocnt += 1

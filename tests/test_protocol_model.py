@@ -15,7 +15,7 @@ def test_shipped_protocol_has_no_violation():
     for trial in range(400):
         rng = random.Random(1234567 + trial)
         items = pm.random_items(rng)
-        pm.Sim(items, rng.choice([4, 8]), rng, hoist=rng.random() < 0.8, two=False).run()
+        pm.Sim(items, rng.choice([4, 8]), rng, hoist=rng.random() < 0.8, two=False, handoffs=rng.choice([2, 2, 3])).run()
 
 
 def test_model_catches_an_early_release():

@@ -74,6 +74,11 @@ struct PItem {
 #ifndef TFA_ISSUER_UNROLL_T
 #define TFA_ISSUER_UNROLL_T 1   // the issuer's main loop is unrolled over the two tiles: compile-time tile index on the issue path
 #endif
+#ifndef TFA_P_HANDOFFS
+#define TFA_P_HANDOFFS 2        // P_t is handed to the issuer after 64 and 128 keys.  A third hand-off after 96 keys (what the
+                                // one-CTA-per-item kernel does) costs the issuer one more barrier wait per tile step: here it
+                                // measured 0.5-1 % slower on cfg3 / cfg4 / non-causal S=4096 (profiles/r02_ab_spin_two_handoffs.txt)
+#endif
 #ifndef TFA_HOIST
 #define TFA_HOIST 1             // 0: never issue the next item's first S early
 #endif
@@ -456,14 +461,16 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
                 if (j + 2 < nmax) mbar_wait(bar(C::KV_FULL, ent_slot(ek + 2u)), ent_par(ek + 2u), p.dbg, SITE_MMA_K);
                 kv_confirmed = true;
               }
+#if TFA_P_HANDOFFS == 3
               mbar_wait(bar(C::P_3Q, t), ppar, p.dbg, SITE_MMA_P3);
               tc_fence_after();
               issue_PV(t, vslot, true, 4, 6, false, false);
+#endif
               mbar_wait(bar(C::P_FULL, t), ppar, p.dbg, SITE_MMA_P);
               TFA_PTRACE_MMA(8 + t);
               st ^= (1u << (2 + t));
               tc_fence_after();
-              issue_PV(t, vslot, true, 6, 8, last_v_user, !has_next);
+              issue_PV(t, vslot, true, TFA_P_HANDOFFS == 3 ? 6 : 4, 8, last_v_user, !has_next);
             }
             // ONE S site: the next KV tile of this item, or -- tile t is done with this item (just now, or in an earlier
             // iteration while the other tile is still running) -- the first S of the NEXT item as soon as its Q_t and K_0
@@ -602,7 +609,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           }
         }
         TFA_PTRACE_SM(4);
-        // ---- P = exp2(s*c - m_ref*c); l += rowsum(P) (fp32, before rounding); pack to 16 bit; three hand-offs ----
+        // ---- P = exp2(s*c - m_ref*c); l += rowsum(P) (fp32, before rounding); pack to 16 bit; TFA_P_HANDOFFS hand-offs ----
         constexpr int kEmuPairsPer8 = kEmuPairsPer8For<D>;
         const float2 c2 = make_float2(c, c);
         const float2 nm2 = make_float2(-m_ref * c, -m_ref * c);
@@ -635,6 +642,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             pk[i] = pack_16x2<IS_BF16>(e.x, e.y);
           }
 #if TFA_DEFER_HANDOFF
+          static_assert(TFA_P_HANDOFFS == 3, "the deferred hand-off experiment assumes three hand-offs");
           if (qt >= 2) {       // quarters 0..qt-1 are stored; their drain was deferred to here, behind this quarter's math
             asm volatile("tcgen05.wait::st.sync.aligned; // after %0" ::"r"(pk[15]) : "memory");
             hand_off(qt - 1);
@@ -647,7 +655,7 @@ fa_fwd_sm100_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
           }
 #else
           tmem_st_x16(tP + qt * 16, pk);
-          if (qt >= 1) {       // hand-offs after keys 0..63 (p_half), 64..95 (p_3q), 96..127 (p_full)
+          if (qt == 1 || qt == 3 || (qt == 2 && TFA_P_HANDOFFS == 3)) {   // after keys 0..63 (p_half), [64..95 (p_3q),] 96..127 (p_full)
             tmem_wait_st();
             hand_off(qt);
             if (qt < 3) TFA_PTRACE_SM(5);
