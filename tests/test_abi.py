@@ -161,3 +161,34 @@ def test_launch_order_mapping_is_a_bijection(built):
                         assert chunk >= prev[0]                      # chunks are taken in order
                     prev = (chunk, split, pr)
                 assert len(seen) == n
+
+
+def test_kernel_selection_rule_on_the_host(built):
+    """choose_kernel (csrc/tfa_api.cu) through its host-callable twin: the shapes of profiles/r02_kernel_choice.md, 148 SMs.
+    0 = one CTA per work item, 4 = persistent.  (TFA_KERNEL forces one kernel and is read once per process.)"""
+    if os.environ.get("TFA_KERNEL"):
+        pytest.skip("TFA_KERNEL forces a kernel in this process")
+    import tfa_ctypes
+    f = tfa_ctypes.lib().tfa_internal_choose_kernel
+    f.argtypes = [ctypes.c_int] * 9
+    f.restype = ctypes.c_int
+    CLASSIC, PERSIST = 0, 4
+
+    def pick(B, H, S, D, causal, nsplit=1, sms=148, n_extra=0, Sk=None):
+        return f(D, int(causal), S, S if Sk is None else Sk, B, H, nsplit, sms, n_extra)
+
+    assert pick(4, 32, 4096, 128, True) == PERSIST          # cfg3
+    assert pick(64, 32, 4096, 128, True) == PERSIST         # cfg5
+    assert pick(1, 32, 16384, 128, True) == CLASSIC         # cfg4: few, very long causal items
+    assert pick(2, 32, 8192, 128, True) == CLASSIC
+    assert pick(64, 32, 8192, 128, True) == PERSIST         # ... but not when there are >= 32 items per SM
+    assert pick(16, 32, 1024, 128, True) == PERSIST
+    assert pick(4, 32, 4096, 128, False) == PERSIST
+    assert pick(2, 32, 8192, 128, False) == PERSIST
+    assert pick(1, 32, 16384, 128, False) == CLASSIC        # 128 KV tiles per item, 13.8 items per SM
+    assert pick(1, 32, 16384, 128, False, nsplit=2) == PERSIST   # split-KV halves the tiles per item
+    assert pick(4, 16, 2048, 64, False) == PERSIST          # cfg2
+    assert pick(1, 32, 16384, 64, False) == CLASSIC
+    assert pick(4, 32, 4096, 64, True) == CLASSIC           # D=64 causal
+    assert pick(32, 32, 512, 64, True) == PERSIST           # ... except S <= 512
+    assert pick(1, 32, 16384, 128, True, n_extra=1) == PERSIST   # the fused exchange always stores through TMA

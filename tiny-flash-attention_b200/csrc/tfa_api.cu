@@ -187,6 +187,14 @@ int choose_kernel(int D, bool causal, long long nitems, long long npairs, long l
   return (npairs >= 32 && few_items) ? KV_CLASSIC : KV_PERSIST;
 }
 
+// the problem as choose_kernel sees it: work items, Q-tile pairs per head, KV tiles per item
+int variant_for(int D, bool causal, int Sq, int Sk, int B, int Hq, int nsplit, int sms, int n_extra) {
+  const long long npairs = (static_cast<long long>(Sq) + 255) / 256;
+  const long long nitems = npairs * B * Hq * nsplit;
+  const long long nkv = ((static_cast<long long>(Sk) + 127) / 128 + nsplit - 1) / nsplit;
+  return choose_kernel(D, causal, nitems, npairs, nkv, sms, n_extra);
+}
+
 // cudaFuncSetAttribute is per device (context) and costs well under a microsecond: set it on every launch instead of
 // caching "done once" per process, which breaks the first launch on a second GPU of the same process.
 template <typename K>
@@ -385,10 +393,7 @@ int fwd_impl(Problem a, void* const* extra_dst = nullptr, int n_extra = 0) {
   if ((rc = make_tmap(&tk, a.k, a.dtype, a.D, a.Sk, a.B, a.Hkv, a.ksb, a.ksh, a.kss))) return rc;
   if ((rc = make_tmap(&tv, a.v, a.dtype, a.D, a.Sk, a.B, a.Hkv, a.ksb, a.ksh, a.kss))) return rc;
 
-  const long long npairs_l = (static_cast<long long>(a.Sq) + 255) / 256;
-  const long long nitems_l = npairs_l * a.B * a.Hq * nsplit;
-  const long long nkv_l = split_tiles;   // KV tiles per item
-  const int variant = choose_kernel(a.D, causal, nitems_l, npairs_l, nkv_l, num_sms(), n_extra);
+  const int variant = variant_for(a.D, causal, a.Sq, a.Sk, a.B, a.Hq, nsplit, num_sms(), n_extra);
   // output tensor maps of the persistent kernels' TMA-store epilogue (16-bit output only): [0] = out, [1..] = peers
   tfa::OutMaps to;
   std::memset(&to, 0, sizeof(to));
@@ -646,6 +651,10 @@ void tfa_host_release(void) {
 unsigned long long tfa_launch_count(void) { return g_launches.load(); }
 // development aid (not in the public header): which kernel the last forward launch used (0 classic, 4 persistent)
 int tfa_internal_last_variant(void) { return g_last_variant.load(); }
+// development aid (not in the public header): the kernel-selection rule as a host function (no device needed)
+int tfa_internal_choose_kernel(int D, int causal, int Sq, int Sk, int B, int Hq, int nsplit, int sms, int n_extra) {
+  return variant_for(D, causal != 0, Sq, Sk, B, Hq, nsplit < 1 ? 1 : nsplit, sms, n_extra);
+}
 // exported for the self tests living in another translation unit
 void tfa_internal_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void* tfa_internal_dbg_dev(void) { init_dbg(); return g_dbg_dev; }
